@@ -1,0 +1,766 @@
+// C ABI of libcrwr_b200.so (see include/crwr_b200.h).  Host-side glue only: workspace layout,
+// kernel launches, status copies.  No device allocation, no CPU compute path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <cmath>
+
+#include "common.cuh"
+#include "propagate.cuh"
+#include "select.cuh"
+#include "transition.cuh"
+#include "finish.cuh"
+
+using namespace crwr;
+
+static thread_local std::string g_err;
+static long long g_launches = 0;
+
+#define CRWR_FAIL(code, ...)                               \
+    do {                                                   \
+        char _b[512];                                      \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);             \
+        g_err = _b;                                        \
+        return (code);                                     \
+    } while (0)
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) CRWR_FAIL(CRWR_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                          \
+    do {                                                                                        \
+        ++g_launches;                                                                           \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess) CRWR_FAIL(CRWR_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+namespace {
+
+constexpr int kNumVariants = 4;
+constexpr int kDenseWarpsPerCta = 4;
+
+struct Layout {
+    size_t state, trace, p_indptr, p_cols, p_vals;
+    size_t it_cols[2], it_vals[2], it_ptr[2], it_len[2];
+    size_t fb_rows, xbuf, cand, merged, counts, counts_scan, total;
+    size_t d_acc, d_oldv, d_ord, d_tbits, d_kbits;
+    size_t k1_row_cnt, k1_col_cnt, k1_col_ptr, k1_col_fill, k1_csc_row, k1_csc_val, k1_scale, k1_iso, k1_row_val;
+    size_t bytes;
+    long long cand_cap;
+    long long dense_warps;
+    long long words;
+};
+
+size_t bump(size_t& off, size_t bytes) {
+    size_t at = (off + 255) & ~(size_t)255;
+    off = at + bytes;
+    return at;
+}
+
+size_t elem(int dtype) { return dtype == CRWR_F64 ? 8 : 4; }
+
+bool make_layout(const crwr_config& c, Layout& L) {
+    const size_t s = elem(c.dtype);
+    const long long n = c.n_contigs;
+    const long long rows = c.row_end - c.row_begin;
+    const long long pcap = c.transition_nnz_cap;
+    const long long cap = c.iterate_cap;
+    size_t off = 0;
+    L.state = bump(off, sizeof(WalkState));
+    L.trace = bump(off, sizeof(crwr_step_record) * kMaxTrace);
+    L.p_indptr = bump(off, 4 * (size_t)(n + 1));
+    L.p_cols = bump(off, 4 * (size_t)pcap);
+    L.p_vals = bump(off, s * (size_t)pcap);
+    for (int b = 0; b < 2; ++b) {
+        L.it_cols[b] = bump(off, 4 * (size_t)cap);
+        L.it_vals[b] = bump(off, s * (size_t)cap);
+        L.it_ptr[b] = bump(off, 8 * (size_t)rows);
+        L.it_len[b] = bump(off, 4 * (size_t)rows);
+    }
+    L.fb_rows = bump(off, 4 * (size_t)rows);
+    // exchange buffer: [extras (kXExtras) | level-0 histogram | level-1 histogram], all uint64
+    L.xbuf = bump(off, 8 * (size_t)(kXExtras + kSelectLevels * kSelectBins));
+    // candidate block [count, successor, keys...]; sharded walks use a small fixed block (all-gathered)
+    if (c.n_shards > 1) L.cand_cap = CRWR_SHARD_CAND;
+    else L.cand_cap = cap / 16 > 65536 ? cap / 16 : 65536;
+    L.cand = bump(off, 8 * (size_t)(kCandHeader + L.cand_cap));
+    L.merged = bump(off, 8 * (size_t)(c.n_shards > 1 ? (long long)c.n_shards * L.cand_cap : 1));
+    L.counts = bump(off, 4 * (size_t)(rows + 1));
+    L.counts_scan = bump(off, 8 * (size_t)(rows + 1));
+    L.total = bump(off, 8);
+    // large-row kernel scratch: as many warps as fit in ~1 GiB, between 8 and 592
+    L.words = (n + 31) / 32;
+    const size_t per_warp = (size_t)n * (2 * s + 4) + (size_t)L.words * 8;
+    long long dw = (long long)(((size_t)1 << 30) / (per_warp ? per_warp : 1));
+    if (dw > 592) dw = 592;
+    if (dw < 8) dw = 8;
+    dw = (dw / kDenseWarpsPerCta) * kDenseWarpsPerCta;
+    L.dense_warps = dw;
+    L.d_acc = bump(off, s * (size_t)n * dw);
+    L.d_oldv = bump(off, s * (size_t)n * dw);
+    L.d_ord = bump(off, 4 * (size_t)n * dw);
+    L.d_tbits = bump(off, 4 * (size_t)L.words * dw);
+    L.d_kbits = bump(off, 4 * (size_t)L.words * dw);
+    // transition-build scratch
+    L.k1_row_cnt = bump(off, 4 * (size_t)(n + 1));
+    L.k1_col_cnt = bump(off, 4 * (size_t)(n + 1));
+    L.k1_col_ptr = bump(off, 4 * (size_t)(n + 1));
+    L.k1_col_fill = bump(off, 4 * (size_t)n);
+    L.k1_csc_row = bump(off, 4 * (size_t)pcap);
+    L.k1_csc_val = bump(off, 8 * (size_t)pcap);
+    L.k1_scale = bump(off, 8 * (size_t)n);
+    L.k1_iso = bump(off, 4 * (size_t)n);
+    L.k1_row_val = bump(off, 8 * (size_t)pcap);
+    L.bytes = (off + 255) & ~(size_t)255;
+    return true;
+}
+
+}  // namespace
+
+struct crwr_handle_s {
+    crwr_config cfg;
+    Layout L;
+    unsigned char* ws;
+    int sm_count;
+    long long p_nnz;
+    bool have_p;
+    bool walking;
+    int steps_enqueued;
+    int variant;                    // hash-table variant of the main propagate kernel
+    int grid[2][kNumVariants];      // persistent grid size per dtype/variant
+    double rp, perc;
+    template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
+};
+
+namespace {
+
+template <typename T, int LOG_H, int KMAX, int WARPS>
+int prepare_variant(int sm_count, int* grid_out) {
+    const size_t smem = PropSmem<T, LOG_H, KMAX>::per_warp * WARPS;
+    cudaError_t e = cudaFuncSetAttribute(propagate_kernel<T, LOG_H, KMAX, WARPS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagate_kernel<T, LOG_H, KMAX, WARPS>, WARPS * 32, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    *grid_out = per_sm * sm_count;
+    return 0;
+}
+
+// variant table: {LOG_H, KMAX, WARPS}
+#define CRWR_VARIANTS(X, T) X(T, 10, 256, 4, 0) X(T, 11, 512, 2, 1) X(T, 12, 1024, 1, 2) X(T, 13, 2048, 1, 3)
+
+template <typename T>
+int prepare_all(crwr_handle_s* h) {
+    int* g = h->grid[sizeof(T) == 8 ? 1 : 0];
+#define X(TT, LH, KM, W, IDX)                                                  \
+    {                                                                          \
+        int e = prepare_variant<TT, LH, KM, W>(h->sm_count, &g[IDX]);          \
+        if (e) return e;                                                       \
+    }
+    CRWR_VARIANTS(X, T)
+#undef X
+    return 0;
+}
+
+template <typename T>
+PropArgs<T> prop_args(crwr_handle_s* h, int parity) {
+    const Layout& L = h->L;
+    PropArgs<T> a;
+    a.p_indptr = h->at<int32_t>(L.p_indptr);
+    a.p_cols = h->at<int32_t>(L.p_cols);
+    a.p_vals = h->at<T>(L.p_vals);
+    const int in = parity, out = parity ^ 1;
+    a.in = IterBuf<T>{h->at<int32_t>(L.it_cols[in]), h->at<T>(L.it_vals[in]), h->at<long long>(L.it_ptr[in]),
+                      h->at<int32_t>(L.it_len[in])};
+    a.out = IterBuf<T>{h->at<int32_t>(L.it_cols[out]), h->at<T>(L.it_vals[out]), h->at<long long>(L.it_ptr[out]),
+                       h->at<int32_t>(L.it_len[out])};
+    a.out_cap = h->cfg.iterate_cap;
+    a.st = h->at<WalkState>(L.state);
+    a.fb_rows = h->at<int32_t>(L.fb_rows);
+    a.n_rows = (int32_t)(h->cfg.row_end - h->cfg.row_begin);
+    a.row_begin = (int32_t)h->cfg.row_begin;
+    a.scale = (T)(1.0 - h->rp);                 // (1 - rp) * matrix: the scalar takes the matrix dtype
+    a.restart = (T)(float)h->rp;                // rp * I with I float32 (utility.py:278)
+    return a;
+}
+
+template <typename T>
+int launch_propagate(crwr_handle_s* h, int parity, cudaStream_t st) {
+    PropArgs<T> a = prop_args<T>(h, parity);
+    const int rows = a.n_rows;
+    const int* g = h->grid[sizeof(T) == 8 ? 1 : 0];
+#define X(TT, LH, KM, W, IDX)                                                                 \
+    if (h->variant == IDX) {                                                                  \
+        int grid = (rows + W - 1) / W;                                                        \
+        if (grid > g[IDX]) grid = g[IDX];                                                     \
+        if (grid < 1) grid = 1;                                                               \
+        const size_t smem = PropSmem<TT, LH, KM>::per_warp * W;                               \
+        propagate_kernel<TT, LH, KM, W><<<grid, W * 32, smem, st>>>(a);                       \
+    }
+    CRWR_VARIANTS(X, T)
+#undef X
+    ++g_launches;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    const Layout& L = h->L;
+    DenseScratch<T> sc;
+    sc.acc = h->at<T>(L.d_acc);
+    sc.oldv = h->at<T>(L.d_oldv);
+    sc.ord = h->at<int32_t>(L.d_ord);
+    sc.tbits = h->at<uint32_t>(L.d_tbits);
+    sc.kbits = h->at<uint32_t>(L.d_kbits);
+    sc.n = h->cfg.n_contigs;
+    sc.words = L.words;
+    propagate_dense_kernel<T, kDenseWarpsPerCta><<<(int)(L.dense_warps / kDenseWarpsPerCta), kDenseWarpsPerCta * 32, 0, st>>>(a, sc);
+    ++g_launches;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return 0;
+}
+
+unsigned long long* hist_ptr(crwr_handle_s* h) { return h->at<unsigned long long>(h->L.xbuf) + kXExtras; }
+
+template <typename T>
+int launch_hist(crwr_handle_s* h, int out_parity, int level, cudaStream_t st) {
+    const Layout& L = h->L;
+    select_hist_kernel<T><<<h->sm_count, 512, 0, st>>>(h->at<T>(L.it_vals[out_parity]), h->at<WalkState>(L.state),
+                                                       hist_ptr(h), level);
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+template <typename T>
+int launch_scan(crwr_handle_s* h, int level, cudaStream_t st) {
+    const Layout& L = h->L;
+    select_scan_kernel<T><<<1, 1024, 0, st>>>(h->at<WalkState>(L.state), hist_ptr(h), level);
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+template <typename T>
+int launch_gather(crwr_handle_s* h, int out_parity, cudaStream_t st) {
+    const Layout& L = h->L;
+    select_gather_kernel<T><<<h->sm_count, 512, 0, st>>>(h->at<T>(L.it_vals[out_parity]), h->at<WalkState>(L.state),
+                                                         h->at<unsigned long long>(L.cand), (unsigned long long)L.cand_cap);
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+// gathered: candidate blocks of all ranks (sharded) or null (own block only)
+template <typename T>
+int launch_finish(crwr_handle_s* h, int do_select, const void* gathered, cudaStream_t st) {
+    const Layout& L = h->L;
+    FinishArgs a;
+    a.st = h->at<WalkState>(L.state);
+    a.hist = h->at<unsigned long long>(L.xbuf);
+    a.xch = h->cfg.n_shards > 1 ? h->at<unsigned long long>(L.xbuf) : nullptr;
+    a.own_block = h->at<unsigned long long>(L.cand);
+    a.blocks = gathered ? (unsigned long long*)gathered : a.own_block;
+    a.n_blocks = gathered ? h->cfg.n_shards : 1;
+    a.block_stride = kCandHeader + L.cand_cap;
+    a.merged = h->at<unsigned long long>(L.merged);
+    a.cand_cap = (unsigned long long)L.cand_cap;
+    a.trace = h->at<crwr_step_record>(L.trace);
+    a.do_select = do_select;
+    finish_step_kernel<T><<<1, 1024, 0, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <typename T>
+int enqueue_step(crwr_handle_s* h, cudaStream_t st) {
+    // the step index and buffer parity are deterministic on the host: every enqueued step either
+    // runs completely or (after the stop rule fired) is skipped completely.
+    const int step = h->steps_enqueued;
+    const int parity = step & 1;
+    if (launch_propagate<T>(h, parity, st)) return -1;
+    if (step >= 1) {
+        if (launch_hist<T>(h, parity ^ 1, 0, st)) return -1;
+        if (launch_scan<T>(h, 0, st)) return -1;
+        if (launch_hist<T>(h, parity ^ 1, 1, st)) return -1;
+        if (launch_scan<T>(h, 1, st)) return -1;
+        if (launch_gather<T>(h, parity ^ 1, st)) return -1;
+    }
+    if (launch_finish<T>(h, step >= 1 ? 1 : 0, nullptr, st)) return -1;
+    h->steps_enqueued = step + 1;
+    return 0;
+}
+
+template <typename T>
+int count_rows(crwr_handle_s* h, int col_limit, int64_t* h_nnz, cudaStream_t st) {
+    const Layout& L = h->L;
+    const int rows = (int)(h->cfg.row_end - h->cfg.row_begin);
+    WalkState host_state;
+    if (cudaMemcpyAsync(&host_state, h->ws + L.state, sizeof(WalkState), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    const int parity = host_state.parity;
+    IterBuf<T> buf{h->at<int32_t>(L.it_cols[parity]), h->at<T>(L.it_vals[parity]), h->at<long long>(L.it_ptr[parity]),
+                   h->at<int32_t>(L.it_len[parity])};
+    const int blocks = (rows * 32 + 255) / 256;
+    result_count_kernel<T><<<blocks > 0 ? blocks : 1, 256, 0, st>>>(buf, h->at<WalkState>(L.state), rows, col_limit,
+                                                                   h->at<int32_t>(L.counts));
+    ++g_launches;
+    exclusive_scan_kernel<int64_t><<<1, 1024, 0, st>>>(h->at<int32_t>(L.counts), h->at<int64_t>(L.counts_scan), rows,
+                                                       h->at<long long>(L.total));
+    ++g_launches;
+    long long total = 0;
+    if (cudaMemcpyAsync(&total, h->ws + L.total, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    *h_nnz = total;
+    return 0;
+}
+
+template <typename T>
+int write_rows(crwr_handle_s* h, int col_limit, int64_t* d_indptr, int32_t* d_indices, void* d_data, cudaStream_t st) {
+    const Layout& L = h->L;
+    const int rows = (int)(h->cfg.row_end - h->cfg.row_begin);
+    WalkState host_state;
+    if (cudaMemcpyAsync(&host_state, h->ws + L.state, sizeof(WalkState), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    const int parity = host_state.parity;
+    IterBuf<T> buf{h->at<int32_t>(L.it_cols[parity]), h->at<T>(L.it_vals[parity]), h->at<long long>(L.it_ptr[parity]),
+                   h->at<int32_t>(L.it_len[parity])};
+    if (cudaMemcpyAsync(d_indptr, h->ws + L.counts_scan, 8 * (size_t)(rows + 1), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return -1;
+    const int blocks = (rows * 32 + 255) / 256;
+    result_write_kernel<T><<<blocks > 0 ? blocks : 1, 256, 0, st>>>(buf, h->at<WalkState>(L.state), rows, col_limit,
+                                                                   h->at<int64_t>(L.counts_scan), d_indices, (T*)d_data);
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t crwr_abi_version(void) { return CRWR_ABI_VERSION; }
+const char* crwr_last_error(void) { return g_err.c_str(); }
+int64_t crwr_launch_count(int32_t reset) {
+    long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+static int check_cfg(const crwr_config* c) {
+    if (!c) CRWR_FAIL(CRWR_ERR_INVALID, "null config");
+    if (c->dtype != CRWR_F32 && c->dtype != CRWR_F64) CRWR_FAIL(CRWR_ERR_INVALID, "dtype must be CRWR_F32 or CRWR_F64");
+    if (c->n_contigs < 1 || c->n_contigs > 2000000000ll) CRWR_FAIL(CRWR_ERR_INVALID, "n_contigs out of range");
+    if (c->n_markers < 1 || c->n_markers > c->n_contigs) CRWR_FAIL(CRWR_ERR_INVALID, "n_markers must be in [1, n_contigs]");
+    if (c->row_begin < 0 || c->row_end > c->n_markers || c->row_begin >= c->row_end)
+        CRWR_FAIL(CRWR_ERR_INVALID, "row range must be a non-empty sub-range of [0, n_markers)");
+    if (c->transition_nnz_cap < 1 || c->transition_nnz_cap > 2000000000ll) CRWR_FAIL(CRWR_ERR_INVALID, "transition_nnz_cap out of range");
+    if (c->iterate_cap < c->row_end - c->row_begin) CRWR_FAIL(CRWR_ERR_INVALID, "iterate_cap smaller than the row count");
+    if (c->n_shards < 1 || c->n_shards > 1024) CRWR_FAIL(CRWR_ERR_INVALID, "n_shards must be in [1, 1024]");
+    if (c->n_shards == 1 && (c->row_begin != 0 || c->row_end != c->n_markers))
+        CRWR_FAIL(CRWR_ERR_INVALID, "an unsharded walk owns all restart rows");
+    return CRWR_OK;
+}
+
+int64_t crwr_workspace_bytes(const crwr_config* cfg) {
+    if (check_cfg(cfg) != CRWR_OK) return -1;
+    Layout L;
+    make_layout(*cfg, L);
+    return (int64_t)L.bytes;
+}
+
+int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace, int64_t workspace_bytes) {
+    if (!out) CRWR_FAIL(CRWR_ERR_INVALID, "null out");
+    int rc = check_cfg(cfg);
+    if (rc != CRWR_OK) return rc;
+    if (!d_workspace) CRWR_FAIL(CRWR_ERR_INVALID, "null workspace");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) CRWR_FAIL(CRWR_ERR_CUDA, "no CUDA device: libcrwr_b200 has no CPU path");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    crwr_handle_s* h = new crwr_handle_s();
+    h->cfg = *cfg;
+    make_layout(*cfg, h->L);
+    if ((int64_t)h->L.bytes > workspace_bytes) {
+        delete h;
+        CRWR_FAIL(CRWR_ERR_INVALID, "workspace too small: need %lld bytes", (long long)h->L.bytes);
+    }
+    h->ws = (unsigned char*)d_workspace;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    h->p_nnz = 0;
+    h->have_p = false;
+    h->walking = false;
+    h->steps_enqueued = 0;
+    h->variant = 0;
+    int e = cfg->dtype == CRWR_F64 ? prepare_all<double>(h) : prepare_all<float>(h);
+    if (e) {
+        delete h;
+        CRWR_FAIL(CRWR_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
+    }
+    *out = h;
+    return CRWR_OK;
+}
+
+int32_t crwr_destroy(crwr_handle h) {
+    delete h;
+    return CRWR_OK;
+}
+
+int32_t crwr_build_transition(crwr_handle h, const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
+                              int64_t nnz, const int32_t* d_new_of_old, int64_t* h_nnz_out, void* stream) {
+    if (!h) CRWR_FAIL(CRWR_ERR_INVALID, "null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout& L = h->L;
+    const long long n = h->cfg.n_contigs;
+    if (nnz < 0 || nnz + n > h->cfg.transition_nnz_cap)
+        CRWR_FAIL(CRWR_ERR_INVALID, "transition_nnz_cap must be at least nnz + n_contigs (self-loops)");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    TransitionScratch sc;
+    sc.row_cnt = h->at<int32_t>(L.k1_row_cnt);
+    sc.col_cnt = h->at<int32_t>(L.k1_col_cnt);
+    sc.col_ptr = h->at<int32_t>(L.k1_col_ptr);
+    sc.col_fill = h->at<int32_t>(L.k1_col_fill);
+    sc.csc_row = h->at<int32_t>(L.k1_csc_row);
+    sc.csc_val = h->at<double>(L.k1_csc_val);
+    sc.scale = h->at<double>(L.k1_scale);
+    sc.isolated = h->at<int32_t>(L.k1_iso);
+    sc.row_val = h->at<double>(L.k1_row_val);
+    sc.total = h->at<long long>(L.total);
+    CUDA_TRY(cudaMemsetAsync(sc.col_cnt, 0, 4 * (size_t)(n + 1), st));
+    CUDA_TRY(cudaMemsetAsync(sc.col_fill, 0, 4 * (size_t)n, st));
+    CUDA_TRY(cudaMemsetAsync(sc.row_cnt, 0, 4 * (size_t)(n + 1), st));
+    const int tb = 256;
+    const int rows_grid = (int)((n + tb - 1) / tb);
+    const int warp_grid = (int)((n * 32 + tb - 1) / tb);
+    transition_count_kernel<<<rows_grid, tb, 0, st>>>(d_indptr, d_indices, d_data, d_new_of_old, n, sc);
+    LAUNCH_CHECK();
+    exclusive_scan_kernel<int32_t><<<1, 1024, 0, st>>>(sc.col_cnt, sc.col_ptr, n, nullptr);
+    LAUNCH_CHECK();
+    transition_scatter_kernel<<<rows_grid, tb, 0, st>>>(d_indptr, d_indices, d_data, d_new_of_old, n, sc);
+    LAUNCH_CHECK();
+    transition_colsum_kernel<<<warp_grid, tb, 0, st>>>(n, sc);
+    LAUNCH_CHECK();
+    exclusive_scan_kernel<int32_t><<<1, 1024, 0, st>>>(sc.row_cnt, h->at<int32_t>(L.p_indptr), n, sc.total);
+    LAUNCH_CHECK();
+    if (h->cfg.dtype == CRWR_F64)
+        transition_fill_kernel<double><<<warp_grid, tb, 0, st>>>(d_indptr, d_indices, d_data, d_new_of_old, n, sc,
+                                                                 h->at<int32_t>(L.p_indptr), h->at<int32_t>(L.p_cols),
+                                                                 h->at<double>(L.p_vals));
+    else
+        transition_fill_kernel<float><<<warp_grid, tb, 0, st>>>(d_indptr, d_indices, d_data, d_new_of_old, n, sc,
+                                                                h->at<int32_t>(L.p_indptr), h->at<int32_t>(L.p_cols),
+                                                                h->at<float>(L.p_vals));
+    LAUNCH_CHECK();
+    long long total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, sc.total, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    h->p_nnz = total;
+    h->have_p = true;
+    if (h_nnz_out) *h_nnz_out = total;
+    return CRWR_OK;
+}
+
+int32_t crwr_set_transition(crwr_handle h, const int32_t* d_indptr, const int32_t* d_indices, const void* d_data,
+                            int64_t nnz, void* stream) {
+    if (!h) CRWR_FAIL(CRWR_ERR_INVALID, "null handle");
+    if (nnz < 0 || nnz > h->cfg.transition_nnz_cap) CRWR_FAIL(CRWR_ERR_INVALID, "nnz exceeds transition_nnz_cap");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout& L = h->L;
+    const size_t s = elem(h->cfg.dtype);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(h->ws + L.p_indptr, d_indptr, 4 * (size_t)(h->cfg.n_contigs + 1), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->ws + L.p_cols, d_indices, 4 * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->ws + L.p_vals, d_data, s * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
+    h->p_nnz = nnz;
+    h->have_p = true;
+    return CRWR_OK;
+}
+
+int32_t crwr_get_transition(crwr_handle h, int32_t* d_indptr, int32_t* d_indices, void* d_data, void* stream) {
+    if (!h || !h->have_p) CRWR_FAIL(CRWR_ERR_STATE, "no transition matrix");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout& L = h->L;
+    const size_t s = elem(h->cfg.dtype);
+    CUDA_TRY(cudaMemcpyAsync(d_indptr, h->ws + L.p_indptr, 4 * (size_t)(h->cfg.n_contigs + 1), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_indices, h->ws + L.p_cols, 4 * (size_t)h->p_nnz, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_data, h->ws + L.p_vals, s * (size_t)h->p_nnz, cudaMemcpyDeviceToDevice, st));
+    return CRWR_OK;
+}
+
+int64_t crwr_transition_nnz(crwr_handle h) { return h && h->have_p ? h->p_nnz : -1; }
+
+int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_t max_steps, void* stream) {
+    if (!h) CRWR_FAIL(CRWR_ERR_INVALID, "null handle");
+    if (!h->have_p) CRWR_FAIL(CRWR_ERR_STATE, "transition matrix not set");
+    if (!(rp >= 0.0 && rp <= 1.0)) CRWR_FAIL(CRWR_ERR_INVALID, "rp must be in [0,1]");
+    if (!(perc >= 0.0 && perc <= 100.0)) CRWR_FAIL(CRWR_ERR_INVALID, "Percentiles must be in the range [0, 100]");
+    if (max_steps < 1 || max_steps > kMaxTrace) CRWR_FAIL(CRWR_ERR_INVALID, "max_steps must be in [1, %d]", kMaxTrace);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout& L = h->L;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    WalkState s0;
+    memset(&s0, 0, sizeof(s0));
+    s0.rp = rp; s0.perc = perc; s0.tol = tol; s0.max_steps = max_steps;
+    CUDA_TRY(cudaMemcpyAsync(h->ws + L.state, &s0, sizeof(s0), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // s0 lives on this stack frame
+    CUDA_TRY(cudaMemsetAsync(h->ws + L.xbuf, 0, 8 * (size_t)(kXExtras + kSelectLevels * kSelectBins), st));
+    {
+        const unsigned long long hdr[2] = {0ull, ~0ull};
+        CUDA_TRY(cudaMemcpyAsync(h->ws + L.cand, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    CUDA_TRY(cudaMemsetAsync(h->ws + L.d_tbits, 0, 4 * (size_t)L.words * L.dense_warps, st));
+    CUDA_TRY(cudaMemsetAsync(h->ws + L.d_kbits, 0, 4 * (size_t)L.words * L.dense_warps, st));
+    const int rows = (int)(h->cfg.row_end - h->cfg.row_begin);
+    if (h->cfg.dtype == CRWR_F64) {
+        IterBuf<double> b{h->at<int32_t>(L.it_cols[0]), h->at<double>(L.it_vals[0]), h->at<long long>(L.it_ptr[0]),
+                          h->at<int32_t>(L.it_len[0])};
+        init_iterate_kernel<double><<<(rows + 255) / 256, 256, 0, st>>>(b, rows, (int)h->cfg.row_begin);
+    } else {
+        IterBuf<float> b{h->at<int32_t>(L.it_cols[0]), h->at<float>(L.it_vals[0]), h->at<long long>(L.it_ptr[0]),
+                         h->at<int32_t>(L.it_len[0])};
+        init_iterate_kernel<float><<<(rows + 255) / 256, 256, 0, st>>>(b, rows, (int)h->cfg.row_begin);
+    }
+    LAUNCH_CHECK();
+    h->rp = rp;
+    h->perc = perc;
+    h->steps_enqueued = 0;
+    h->walking = true;
+    h->variant = 0;
+    return CRWR_OK;
+}
+
+int32_t crwr_set_variant(crwr_handle h, int32_t variant) {
+    if (!h || variant < 0 || variant >= kNumVariants) CRWR_FAIL(CRWR_ERR_INVALID, "variant out of range");
+    h->variant = variant;
+    return CRWR_OK;
+}
+
+int32_t crwr_walk_enqueue(crwr_handle h, int32_t n_steps, void* stream) {
+    if (!h || !h->walking) CRWR_FAIL(CRWR_ERR_STATE, "crwr_walk_init first");
+    if (h->cfg.n_shards != 1)
+        CRWR_FAIL(CRWR_ERR_STATE, "crwr_walk_enqueue is for unsharded walks; use the crwr_step_* calls");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    for (int i = 0; i < n_steps; ++i) {
+        int e = h->cfg.dtype == CRWR_F64 ? enqueue_step<double>(h, st) : enqueue_step<float>(h, st);
+        if (e) CRWR_FAIL(CRWR_ERR_CUDA, "step launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    return CRWR_OK;
+}
+
+// ---- sharded walk: the caller interleaves these with its collectives ----------
+#define STEP_PROLOGUE()                                                                  \
+    if (!h || !h->walking) CRWR_FAIL(CRWR_ERR_STATE, "crwr_walk_init first");             \
+    cudaStream_t st = (cudaStream_t)stream;                                               \
+    CUDA_TRY(cudaSetDevice(h->cfg.device));                                               \
+    const bool f64 = h->cfg.dtype == CRWR_F64;                                            \
+    const int parity = h->steps_enqueued & 1;                                             \
+    (void)parity; (void)f64;
+
+int32_t crwr_step_propagate(crwr_handle h, void* stream) {
+    STEP_PROLOGUE();
+    int e = f64 ? launch_propagate<double>(h, parity, st) : launch_propagate<float>(h, parity, st);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "propagate launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    pack_exchange_kernel<<<1, 32, 0, st>>>(h->at<WalkState>(h->L.state), h->at<unsigned long long>(h->L.xbuf));
+    LAUNCH_CHECK();
+    return CRWR_OK;
+}
+int32_t crwr_step_hist(crwr_handle h, int32_t level, void* stream) {
+    STEP_PROLOGUE();
+    if (level < 0 || level >= kSelectLevels) CRWR_FAIL(CRWR_ERR_INVALID, "level out of range");
+    int e = f64 ? launch_hist<double>(h, parity ^ 1, level, st) : launch_hist<float>(h, parity ^ 1, level, st);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "hist launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return CRWR_OK;
+}
+int32_t crwr_step_scan(crwr_handle h, int32_t level, void* stream) {
+    STEP_PROLOGUE();
+    if (level < 0 || level >= kSelectLevels) CRWR_FAIL(CRWR_ERR_INVALID, "level out of range");
+    int e = f64 ? launch_scan<double>(h, level, st) : launch_scan<float>(h, level, st);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return CRWR_OK;
+}
+int32_t crwr_step_gather(crwr_handle h, void* stream) {
+    STEP_PROLOGUE();
+    int e = f64 ? launch_gather<double>(h, parity ^ 1, st) : launch_gather<float>(h, parity ^ 1, st);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "gather launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return CRWR_OK;
+}
+int32_t crwr_step_finish(crwr_handle h, const void* d_gathered_blocks, void* stream) {
+    STEP_PROLOGUE();
+    const int do_select = h->steps_enqueued >= 1 ? 1 : 0;
+    if (do_select && h->cfg.n_shards > 1 && !d_gathered_blocks)
+        CRWR_FAIL(CRWR_ERR_INVALID, "a sharded step needs the all-gathered candidate blocks");
+    const void* g = (do_select && h->cfg.n_shards > 1) ? d_gathered_blocks : nullptr;
+    int e = f64 ? launch_finish<double>(h, do_select, g, st) : launch_finish<float>(h, do_select, g, st);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "finish launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->steps_enqueued += 1;
+    return CRWR_OK;
+}
+void* crwr_exchange_ptr(crwr_handle h, int32_t which) {
+    if (!h) return nullptr;
+    const Layout& L = h->L;
+    if (which == 0) return h->ws + L.xbuf;
+    if (which == 1) return h->ws + L.xbuf + 8 * (size_t)(kXExtras + kSelectBins);
+    if (which == 2) return h->ws + L.cand;
+    return nullptr;
+}
+int64_t crwr_exchange_bytes(crwr_handle h, int32_t which) {
+    if (!h) return -1;
+    if (which == 0) return 8 * (int64_t)(kXExtras + kSelectBins);
+    if (which == 1) return 8 * (int64_t)kSelectBins;
+    if (which == 2) return 8 * (int64_t)(kCandHeader + h->L.cand_cap);
+    return -1;
+}
+
+int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
+    if (!h || !out) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    WalkState s;
+    CUDA_TRY(cudaMemcpyAsync(&s, h->ws + h->L.state, sizeof(s), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    out->steps_done = s.step;
+    out->stop_reason = s.done ? s.stop_reason : CRWR_STOP_RUNNING;
+    out->capacity_overflow = s.capacity_overflow | (s.select_overflow << 1);
+    out->fallback_rows = s.last_fallback_rows;
+    out->nnz_iterate = (int64_t)s.cursor;
+    out->max_row_len = s.max_row_len;
+    out->max_kept = s.last_max_kept;
+    out->last_cut = s.cut;
+    out->last_delta = s.last_delta;
+    if (s.done && s.stop_reason == CRWR_STOP_RUNNING) out->stop_reason = CRWR_STOP_MAX_STEPS;
+    // the host-side step counter follows the device: steps enqueued past the stop were skipped
+    if (s.done) h->steps_enqueued = s.step;
+    if (s.capacity_overflow) CRWR_FAIL(CRWR_ERR_CAPACITY, "iterate buffer overflow (capacity %lld entries)", (long long)h->cfg.iterate_cap);
+    if (s.select_overflow) CRWR_FAIL(CRWR_ERR_CAPACITY, "percentile candidate buffer overflow");
+    return CRWR_OK;
+}
+
+int32_t crwr_walk_trace(crwr_handle h, crwr_step_record* out, int32_t cap, void* stream) {
+    if (!h || !out) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int n = cap < kMaxTrace ? cap : kMaxTrace;
+    CUDA_TRY(cudaMemcpyAsync(out, h->ws + h->L.trace, sizeof(crwr_step_record) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CRWR_OK;
+}
+
+int32_t crwr_result_count(crwr_handle h, int64_t* h_nnz, void* stream) {
+    if (!h || !h_nnz) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    int e = h->cfg.dtype == CRWR_F64 ? count_rows<double>(h, (int)h->cfg.n_markers, h_nnz, (cudaStream_t)stream)
+                                     : count_rows<float>(h, (int)h->cfg.n_markers, h_nnz, (cudaStream_t)stream);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "result count failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return CRWR_OK;
+}
+int32_t crwr_result_write(crwr_handle h, int64_t* d_indptr, int32_t* d_indices, void* d_data, void* stream) {
+    if (!h) CRWR_FAIL(CRWR_ERR_INVALID, "null handle");
+    int e = h->cfg.dtype == CRWR_F64 ? write_rows<double>(h, (int)h->cfg.n_markers, d_indptr, d_indices, d_data, (cudaStream_t)stream)
+                                     : write_rows<float>(h, (int)h->cfg.n_markers, d_indptr, d_indices, d_data, (cudaStream_t)stream);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "result write failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return CRWR_OK;
+}
+int32_t crwr_iterate_count(crwr_handle h, int64_t* h_nnz, void* stream) {
+    if (!h || !h_nnz) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    int e = h->cfg.dtype == CRWR_F64 ? count_rows<double>(h, 0x7fffffff, h_nnz, (cudaStream_t)stream)
+                                     : count_rows<float>(h, 0x7fffffff, h_nnz, (cudaStream_t)stream);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "iterate count failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return CRWR_OK;
+}
+int32_t crwr_iterate_write(crwr_handle h, int64_t* d_indptr, int32_t* d_indices, void* d_data, void* stream) {
+    if (!h) CRWR_FAIL(CRWR_ERR_INVALID, "null handle");
+    int e = h->cfg.dtype == CRWR_F64 ? write_rows<double>(h, 0x7fffffff, d_indptr, d_indices, d_data, (cudaStream_t)stream)
+                                     : write_rows<float>(h, 0x7fffffff, d_indptr, d_indices, d_data, (cudaStream_t)stream);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "iterate write failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return CRWR_OK;
+}
+
+}  // extern "C"
+
+// ---- symmetrise ------------------------------------------------------------------------------
+namespace {
+template <typename T>
+size_t sym_layout(int64_t m, int64_t nnz, SymScratch<T>* sc, unsigned char* base) {
+    size_t off = 0;
+    size_t a;
+    a = bump(off, 4 * (size_t)(m + 1)); if (sc) sc->t_cnt = (int32_t*)(base + a);
+    a = bump(off, 8 * (size_t)(m + 1)); if (sc) sc->t_ptr = (int64_t*)(base + a);
+    a = bump(off, 4 * (size_t)(m + 1)); if (sc) sc->t_fill = (int32_t*)(base + a);
+    a = bump(off, 4 * (size_t)(nnz + 1)); if (sc) sc->t_col = (int32_t*)(base + a);
+    a = bump(off, sizeof(T) * (size_t)(nnz + 1)); if (sc) sc->t_val = (T*)(base + a);
+    a = bump(off, 4 * (size_t)(m + 1)); if (sc) sc->e_cnt = (int32_t*)(base + a);
+    a = bump(off, 8 * (size_t)(m + 1)); if (sc) sc->e_ptr = (int64_t*)(base + a);
+    a = bump(off, sizeof(T) * (size_t)(m + 1)); if (sc) sc->b = (T*)(base + a);
+    a = bump(off, 8); if (sc) sc->total = (long long*)(base + a);
+    return (off + 255) & ~(size_t)255;
+}
+
+template <typename T>
+int sym_count(int64_t m, const int64_t* ip, const int32_t* ix, const T* data, int64_t nnz, void* scratch,
+              int64_t* h_out, cudaStream_t st) {
+    SymScratch<T> sc;
+    sym_layout<T>(m, nnz, &sc, (unsigned char*)scratch);
+    if (cudaMemsetAsync(sc.t_cnt, 0, 4 * (size_t)(m + 1), st) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(sc.t_fill, 0, 4 * (size_t)(m + 1), st) != cudaSuccess) return -1;
+    const int blocks = (int)((m * 32 + 255) / 256);
+    sym_count_cols_kernel<T><<<blocks, 256, 0, st>>>((int)m, ip, ix, sc);
+    ++g_launches;
+    exclusive_scan_kernel<int64_t><<<1, 1024, 0, st>>>(sc.t_cnt, sc.t_ptr, m, nullptr);
+    ++g_launches;
+    sym_scatter_kernel<T><<<blocks, 256, 0, st>>>((int)m, ip, ix, data, sc);
+    ++g_launches;
+    sym_sort_count_kernel<T><<<blocks, 256, 0, st>>>((int)m, ip, ix, sc);
+    ++g_launches;
+    exclusive_scan_kernel<int64_t><<<1, 1024, 0, st>>>(sc.e_cnt, sc.e_ptr, m, sc.total);
+    ++g_launches;
+    long long total = 0;
+    if (cudaMemcpyAsync(&total, sc.total, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    *h_out = total;
+    return 0;
+}
+
+template <typename T>
+int sym_write(int64_t m, const int64_t* ip, const int32_t* ix, const T* data, int64_t nnz, void* scratch,
+              int64_t* out_ip, int32_t* out_ix, T* out_data, cudaStream_t st) {
+    SymScratch<T> sc;
+    sym_layout<T>(m, nnz, &sc, (unsigned char*)scratch);
+    if (cudaMemcpyAsync(out_ip, sc.e_ptr, 8 * (size_t)(m + 1), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+    const int blocks = (int)((m * 32 + 255) / 256);
+    sym_merge_kernel<T><<<blocks, 256, 0, st>>>((int)m, ip, ix, data, sc, sc.e_ptr, out_ix, out_data);
+    ++g_launches;
+    sym_scale_kernel<T><<<blocks, 256, 0, st>>>((int)m, sc.e_ptr, out_ix, out_data, sc.b);
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+}  // namespace
+
+extern "C" {
+
+int64_t crwr_symmetrise_scratch_bytes(int64_t m, int64_t nnz) {
+    if (m < 1 || nnz < 0) return -1;
+    return (int64_t)sym_layout<double>(m, nnz, nullptr, nullptr);
+}
+
+int32_t crwr_symmetrise_count(int32_t dtype, int64_t m, const int64_t* d_indptr, const int32_t* d_indices, const void* d_data,
+                              int64_t nnz, void* d_scratch, int64_t scratch_bytes, int64_t* h_nnz_out, void* stream) {
+    if (m < 1 || nnz < 0 || !d_scratch || !h_nnz_out) CRWR_FAIL(CRWR_ERR_INVALID, "bad argument");
+    if (scratch_bytes < crwr_symmetrise_scratch_bytes(m, nnz)) CRWR_FAIL(CRWR_ERR_INVALID, "scratch too small");
+    int e = dtype == CRWR_F64 ? sym_count<double>(m, d_indptr, d_indices, (const double*)d_data, nnz, d_scratch, h_nnz_out, (cudaStream_t)stream)
+                              : sym_count<float>(m, d_indptr, d_indices, (const float*)d_data, nnz, d_scratch, h_nnz_out, (cudaStream_t)stream);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "symmetrise count failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return CRWR_OK;
+}
+
+int32_t crwr_symmetrise_write(int32_t dtype, int64_t m, const int64_t* d_indptr, const int32_t* d_indices, const void* d_data,
+                              int64_t nnz, void* d_scratch, int64_t scratch_bytes, int64_t* d_out_indptr, int32_t* d_out_indices,
+                              void* d_out_data, void* stream) {
+    if (m < 1 || nnz < 0 || !d_scratch) CRWR_FAIL(CRWR_ERR_INVALID, "bad argument");
+    if (scratch_bytes < crwr_symmetrise_scratch_bytes(m, nnz)) CRWR_FAIL(CRWR_ERR_INVALID, "scratch too small");
+    int e = dtype == CRWR_F64 ? sym_write<double>(m, d_indptr, d_indices, (const double*)d_data, nnz, d_scratch, d_out_indptr, d_out_indices, (double*)d_out_data, (cudaStream_t)stream)
+                              : sym_write<float>(m, d_indptr, d_indices, (const float*)d_data, nnz, d_scratch, d_out_indptr, d_out_indices, (float*)d_out_data, (cudaStream_t)stream);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "symmetrise write failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return CRWR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+// Shared device-side definitions for libcrwr_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/crwr_b200.h"
+
+namespace crwr {
+
+constexpr int kSelectBits = 12;                 // radix digit of the percentile select
+constexpr int kSelectBins = 1 << kSelectBits;   // 4096
+constexpr int kSelectLevels = 2;                // full-data histogram levels before the gather
+constexpr int kCandSmem = 4096;                 // candidates ranked inside shared memory
+constexpr int kMaxTrace = 4096;                 // per-step records kept on the device
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// Exact (non-contracted) arithmetic.  scipy's csr_matmat does `sums[j] += v * B[k,j]` as a
+// separate multiply and add (x86-64 baseline wheels carry no FMA), so these must never fuse.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+
+// Order-preserving map float -> unsigned (all finite values, either sign).
+template <typename T> struct KeyOf;
+template <> struct KeyOf<float> {
+    typedef uint32_t type;
+    static constexpr int bits = 32;
+    __device__ __forceinline__ static uint32_t enc(float v) {
+        uint32_t b = __float_as_uint(v);
+        return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+    }
+    __device__ __forceinline__ static float dec(uint32_t k) {
+        uint32_t b = (k >> 31) ? (k ^ 0x80000000u) : ~k;
+        return __uint_as_float(b);
+    }
+};
+template <> struct KeyOf<double> {
+    typedef uint64_t type;
+    static constexpr int bits = 64;
+    __device__ __forceinline__ static uint64_t enc(double v) {
+        uint64_t b = (uint64_t)__double_as_longlong(v);
+        return b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+    }
+    __device__ __forceinline__ static double dec(uint64_t k) {
+        uint64_t b = (k >> 63) ? (k ^ 0x8000000000000000ull) : ~k;
+        return __longlong_as_double((long long)b);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Walk state, resident in the workspace.  Written only by single-thread sections of kernels.
+// ---------------------------------------------------------------------------------------------
+struct WalkState {
+    // parameters (crwr_walk_init)
+    double rp, perc, tol;
+    int32_t max_steps;
+    // progress
+    int32_t step;            // index of the step being / about to be executed
+    int32_t done;            // stop rule fired
+    int32_t stop_reason;
+    int32_t plateau;         // utility.py:298-299 cumulative counter
+    double delta_prev;       // utility.py:301
+    int32_t parity;          // buffer holding the iterate the next propagate reads
+    int32_t cut_on;          // 1: entries <= cut are dropped when the iterate is read (lazy cut)
+    double cut;              // value of the last applied cut (exact in the walk dtype)
+    // per-step counters, reset by the finish kernel
+    unsigned long long cursor;      // entries allocated in the output buffer (= local nnz_new)
+    unsigned long long nnz_in;      // kept entries read this step (local)
+    unsigned int row_counter;       // dynamic row scheduler of the main propagate kernel
+    unsigned int fb_counter;        // ... of the large-row kernel
+    unsigned int fb_count;          // rows queued for the large-row kernel
+    int32_t max_row_len;
+    int32_t max_kept;               // longest kept list read this step
+    int32_t last_max_kept;
+    int32_t capacity_overflow;      // sticky
+    int32_t select_overflow;        // sticky: candidate buffer overflow
+    // select
+    unsigned long long n_total;     // global number of values (sum of level-0 histogram)
+    unsigned long long rank_k;      // floor of the virtual index
+    unsigned long long below;       // values strictly below the current prefix bin
+    unsigned long long prefix;      // accumulated digits (level 0 in the high bits)
+    unsigned long long bin_count;   // population of the selected bin
+    double gamma;                   // fractional part of the virtual index (walk dtype precision)
+    int32_t clamp_last;             // virtual index >= n-1: both order statistics are the maximum
+    int32_t last_fallback_rows;
+    double last_delta;
+    unsigned long long sq_limb[3];  // sum of per-row ||dQ||^2 in 2^-64 fixed point, 32-bit limbs
+};
+
+// Exchange block 0 of a sharded walk: level-0 histogram followed by these extras (all uint64, SUM).
+constexpr int kXSq0 = 0, kXSq1 = 1, kXSq2 = 2, kXNnzIn = 3, kXNnzNew = 4, kXCapOvf = 5, kXSelOvf = 6, kXFallback = 7;
+constexpr int kXExtras = 8;
+// Candidate block: [count, successor key, keys...] (uint64).
+constexpr int kCandHeader = 2;
+
+template <typename T>
+struct IterBuf {
+    int32_t* cols;
+    T* vals;
+    long long* row_ptr;
+    int32_t* row_len;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Warp helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+template <typename K> __device__ __forceinline__ K warp_min(K v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        K w = __shfl_xor_sync(kFull, v, o);
+        v = w < v ? w : v;
+    }
+    return v;
+}
+
+// Ascending sort of (key[i], val[i]) for i < n by one warp; all-ascending bitonic network with
+// "flip" first stages, valid for any n (out-of-range partners act as +inf).  Keys are unique.
+template <typename K, typename V>
+__device__ __forceinline__ void warp_sort_pairs(K* key, V* val, int n) {
+    const int lane = lane_id();
+    for (int k = 2; (k >> 1) < n; k <<= 1) {
+        for (int i = lane; i < n; i += 32) {
+            int l = i ^ (k - 1);
+            if (l > i && l < n) {
+                K a = key[i], b = key[l];
+                if (b < a) { key[i] = b; key[l] = a; V t = val[i]; val[i] = val[l]; val[l] = t; }
+            }
+        }
+        __syncwarp();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int i = lane; i < n; i += 32) {
+                int l = i ^ j;
+                if (l > i && l < n) {
+                    K a = key[i], b = key[l];
+                    if (b < a) { key[i] = b; key[l] = a; V t = val[i]; val[i] = val[l]; val[l] = t; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// numpy's pairwise summation as np.add.reduceat applies it to one contiguous segment:
+// x[0] + pairwise(x[1:])  (numpy/_core/src/umath/loops_utils.h.src, PW_BLOCKSIZE 128).
+template <typename T>
+__device__ T np_pairwise(const T* x, long long n) {
+    if (n < 8) {
+        T r = (T)0;
+        for (long long i = 0; i < n; ++i) r = add_rn(r, x[i]);
+        return r;
+    } else if (n <= 128) {
+        T r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = x[j];
+        long long i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = add_rn(r[j], x[i + j]);
+        }
+        T res = add_rn(add_rn(add_rn(r[0], r[1]), add_rn(r[2], r[3])), add_rn(add_rn(r[4], r[5]), add_rn(r[6], r[7])));
+        for (; i < n; ++i) res = add_rn(res, x[i]);
+        return res;
+    } else {
+        long long n2 = n / 2;
+        n2 -= n2 % 8;
+        return add_rn(np_pairwise<T>(x, n2), np_pairwise<T>(x + n2, n - n2));
+    }
+}
+template <typename T>
+__device__ T np_segment_sum(const T* x, long long n) {   // n >= 1
+    if (n == 1) return x[0];
+    return add_rn(x[0], np_pairwise<T>(x + 1, n - 1));
+}
+
+}  // namespace crwr

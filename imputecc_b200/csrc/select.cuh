@@ -1,0 +1,386 @@
+// K3: the per-step percentile cut  np.percentile(Q.data, perc)  (utility.py:287) as an exact
+// radix select on order-preserving integer keys, plus the step's stop logic (utility.py:293-304).
+//
+//   level 0 histogram (top 12 key bits, all values)  -> scan: total n, virtual index, target bin
+//   level 1 histogram (next 12 bits, values in bin)  -> scan: 24-bit prefix of x_(k)
+//   gather: values whose 24-bit prefix matches -> candidate list; min key above the bin -> successor
+//   finish: rank candidates -> x_(k), x_(k+1) -> numpy 'linear' interpolation -> cut; delta; stop rules
+//
+// Histograms are plain integer counts, so a sharded walk only has to SUM them across ranks
+// (and concatenate candidates) for every rank to derive the identical cut.
+#pragma once
+#include "common.cuh"
+
+namespace crwr {
+
+template <typename T>
+__global__ void __launch_bounds__(512) select_hist_kernel(const T* __restrict__ vals, WalkState* st,
+                                                          unsigned long long* __restrict__ hist, int level) {
+    typedef KeyOf<T> KO;
+    typedef typename KO::type K;
+    __shared__ unsigned int sh[kSelectBins];
+    if (st->done) return;
+    for (int i = threadIdx.x; i < kSelectBins; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    const long long n = (long long)st->cursor;
+    const K prefix = (K)st->prefix;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const K key = KO::enc(vals[i]);
+        if (level == 0) {
+            atomicAdd(&sh[(unsigned)(key >> (KO::bits - kSelectBits))], 1u);
+        } else {
+            if ((key >> (KO::bits - kSelectBits)) == prefix)
+                atomicAdd(&sh[(unsigned)(key >> (KO::bits - 2 * kSelectBits)) & (kSelectBins - 1)], 1u);
+        }
+    }
+    __syncthreads();
+    unsigned long long* out = hist + (size_t)level * kSelectBins;
+    for (int i = threadIdx.x; i < kSelectBins; i += blockDim.x) {
+        unsigned int c = sh[i];
+        if (c) atomicAdd(&out[i], (unsigned long long)c);
+    }
+}
+
+// Single CTA of 1024 threads.  hist already holds the GLOBAL counts of this level.
+template <typename T>
+__global__ void __launch_bounds__(1024) select_scan_kernel(WalkState* st, const unsigned long long* __restrict__ hist,
+                                                           int level) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long s_total;
+    if (st->done) return;
+    const unsigned long long* h = hist + (size_t)level * kSelectBins;
+    const int t = threadIdx.x;
+    unsigned long long c[4];
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c[i] = h[t * 4 + i]; mine += c[i]; }
+    // inclusive scan of per-thread totals
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long v = __shfl_up_sync(kFull, incl, o);
+        if ((t & 31) >= o) incl += v;
+    }
+    if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        unsigned long long w = warp_tot[t];
+        unsigned long long wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long v = __shfl_up_sync(kFull, wi, o);
+            if (t >= o) wi += v;
+        }
+        warp_tot[t] = wi - w;   // exclusive
+        if (t == 31) s_total = wi;
+    }
+    __syncthreads();
+    const unsigned long long excl = warp_tot[t >> 5] + incl - mine;
+
+    if (level == 0) {
+        if (t == 0) {
+            // numpy percentile(), method 'linear': q and the virtual index live in the data dtype
+            const unsigned long long n = s_total;
+            const T q = div_rn((T)st->perc, (T)100);
+            const T nm1 = (T)(n - 1);
+            const T v = mul_rn(nm1, q);
+            const T kf = floor(v);
+            unsigned long long k = (unsigned long long)kf;
+            int clamp = 0;
+            T g = sub_rn(v, kf);
+            if (v >= nm1 || k >= n - 1) { clamp = 1; k = n - 1; g = (T)0; }
+            st->n_total = n;
+            st->rank_k = k;
+            st->gamma = (double)g;
+            st->clamp_last = clamp;
+            st->below = 0;
+            st->prefix = 0;
+        }
+        __syncthreads();
+    }
+    const unsigned long long below0 = st->below;
+    const unsigned long long prefix0 = st->prefix;
+    const unsigned long long target = st->rank_k - below0;      // rank inside the current bin set
+    __syncthreads();                                            // all reads precede the single write
+    unsigned long long run = excl;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (target >= run && target < run + c[i]) {
+            st->below = below0 + run;      // exactly one thread matches
+            st->prefix = (prefix0 << kSelectBits) | (unsigned long long)(t * 4 + i);
+            st->bin_count = c[i];
+        }
+        run += c[i];
+    }
+}
+
+// Candidate block layout (uint64): [0] count, [1] smallest key above the candidate bin, [2..] keys.
+template <typename T>
+__global__ void __launch_bounds__(512) select_gather_kernel(const T* __restrict__ vals, WalkState* st,
+                                                            unsigned long long* __restrict__ block,
+                                                            unsigned long long cand_cap) {
+    typedef KeyOf<T> KO;
+    typedef typename KO::type K;
+    if (st->done) return;
+    const long long n = (long long)st->cursor;
+    const K prefix = (K)st->prefix;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    K best = ~(K)0;
+    bool have = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const K key = KO::enc(vals[i]);
+        const K p = key >> (KO::bits - 2 * kSelectBits);
+        if (p == prefix) {
+            unsigned long long idx = atomicAdd(&block[0], 1ull);
+            if (idx < cand_cap) block[kCandHeader + idx] = (unsigned long long)key;
+        } else if (p > prefix) {
+            if (!have || key < best) best = key;
+            have = true;
+        }
+    }
+    unsigned long long b64 = have ? (unsigned long long)best : ~0ull;
+    b64 = warp_min(b64);
+    if ((threadIdx.x & 31) == 0 && b64 != ~0ull) atomicMin(&block[1], b64);
+}
+
+// Block-wide radix select of local rank r among cand[0..c) (keys share their top 24 bits), 8 bits at
+// a time.  Returns the key, the number of candidates strictly below it and its multiplicity.
+template <int KBITS>
+__device__ void block_radix_select(const unsigned long long* cand, unsigned long long c, unsigned long long r,
+                                   unsigned int* sh_hist, unsigned long long* sh_io, unsigned long long& key_out,
+                                   unsigned long long& below_out, unsigned long long& dup_out) {
+    int remaining = KBITS - 2 * kSelectBits;
+    unsigned long long known = 0, mask = 0, below = 0, cnt = c;
+    while (remaining > 0) {
+        const int d = remaining >= 8 ? 8 : remaining;
+        const int shift = remaining - d;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) sh_hist[i] = 0u;
+        __syncthreads();
+        for (unsigned long long i = threadIdx.x; i < c; i += blockDim.x) {
+            const unsigned long long key = cand[i];
+            if ((key & mask) == known) atomicAdd(&sh_hist[(unsigned)(key >> shift) & ((1u << d) - 1u)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long run = below;
+            unsigned int b = 0;
+            for (; b + 1 < (1u << d); ++b) {
+                unsigned long long nb = run + sh_hist[b];
+                if (r < nb) break;
+                run = nb;
+            }
+            sh_io[0] = run;
+            sh_io[1] = b;
+            sh_io[2] = sh_hist[b];
+        }
+        __syncthreads();
+        below = sh_io[0];
+        known |= sh_io[1] << shift;
+        mask |= ((unsigned long long)((1u << d) - 1u)) << shift;
+        cnt = sh_io[2];
+        remaining = shift;
+        __syncthreads();
+    }
+    key_out = (cand[0] & ~mask) | known;   // the top 24 bits are common to all candidates
+    below_out = below;
+    dup_out = cnt;
+}
+
+struct FinishArgs {
+    WalkState* st;
+    unsigned long long* hist;             // [levels][4096], cleared here for the next step
+    const unsigned long long* xch;        // sharded: all-reduced extras (kX*), else null -> read WalkState
+    unsigned long long* blocks;           // candidate blocks: n_blocks of block_stride uint64 each
+    int32_t n_blocks;
+    long long block_stride;
+    unsigned long long* own_block;        // this rank's block, reset for the next step
+    unsigned long long* merged;           // scratch to concatenate blocks when n_blocks > 1 or for the slow path
+    unsigned long long cand_cap;          // keys per block
+    crwr_step_record* trace;
+    int32_t do_select;                    // 0 on step 0 (utility.py:286)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024) finish_step_kernel(FinishArgs a) {
+    typedef KeyOf<T> KO;
+    typedef typename KO::type K;
+    __shared__ unsigned long long sk[kCandSmem];
+    __shared__ unsigned int sh_hist[256];
+    __shared__ unsigned long long sh_io[4];
+    __shared__ unsigned long long wbest[32];
+    __shared__ unsigned long long s_xk, s_xk1, s_total, s_succ;
+    __shared__ int s_have1, s_ovf;
+    WalkState* st = a.st;
+    if (st->done) return;
+    const int t = threadIdx.x;
+
+    if (t == 0) { s_have1 = 0; s_xk = 0; s_xk1 = 0; s_ovf = 0; }
+    __syncthreads();
+
+    if (a.do_select) {
+        // ---- concatenate the candidate blocks (one per rank)
+        if (t == 0) {
+            unsigned long long tot = 0, succ = ~0ull;
+            int ovf = 0;
+            for (int b = 0; b < a.n_blocks; ++b) {
+                const unsigned long long* blk = a.blocks + (long long)b * a.block_stride;
+                if (blk[0] > a.cand_cap) ovf = 1;
+                tot += blk[0];
+                succ = blk[1] < succ ? blk[1] : succ;
+            }
+            s_total = tot; s_succ = succ; s_ovf = ovf;
+        }
+        __syncthreads();
+        const unsigned long long c = s_total;
+        const unsigned long long r = st->rank_k - st->below;
+        const unsigned long long* cand = a.blocks + kCandHeader;
+        if (!s_ovf && a.n_blocks > 1) {
+            unsigned long long off = 0;
+            for (int b = 0; b < a.n_blocks; ++b) {
+                const unsigned long long* blk = a.blocks + (long long)b * a.block_stride;
+                const unsigned long long cb = blk[0];
+                for (unsigned long long i = t; i < cb; i += blockDim.x) a.merged[off + i] = blk[kCandHeader + i];
+                off += cb;
+            }
+            __syncthreads();
+            cand = a.merged;
+        }
+        if (s_ovf) {
+            // handled below (sticky error)
+        } else if (c <= (unsigned long long)kCandSmem) {
+            for (unsigned int i = t; i < c; i += blockDim.x) sk[i] = cand[i];
+            __syncthreads();
+            for (unsigned int i = t; i < c; i += blockDim.x) {
+                const unsigned long long me = sk[i];
+                unsigned long long rank = 0;
+                for (unsigned int j = 0; j < c; ++j) {
+                    const unsigned long long o = sk[j];
+                    rank += (o < me) || (o == me && j < i);
+                }
+                if (rank == r) s_xk = me;
+                if (rank == r + 1) { s_xk1 = me; s_have1 = 1; }
+            }
+            __syncthreads();
+        } else {
+            unsigned long long key, below, dup;
+            block_radix_select<KO::bits>(cand, c, r, sh_hist, sh_io, key, below, dup);
+            if (r + 1 < below + dup) {
+                if (t == 0) { s_xk = key; s_xk1 = key; s_have1 = 1; }
+            } else {
+                unsigned long long best = ~0ull;
+                for (unsigned long long i = t; i < c; i += blockDim.x) {
+                    const unsigned long long o = cand[i];
+                    if (o > key && o < best) best = o;
+                }
+                best = warp_min(best);
+                if ((t & 31) == 0) wbest[t >> 5] = best;
+                __syncthreads();
+                if (t == 0) {
+                    unsigned long long b = ~0ull;
+                    for (int w = 0; w < 32; ++w) b = wbest[w] < b ? wbest[w] : b;
+                    s_xk = key;
+                    if (below + dup < c) { s_xk1 = b; s_have1 = 1; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    if (t == 0) {
+        double cut = __longlong_as_double(0x7ff8000000000000ll);   // NaN: no cut computed
+        int cut_applied = 0;
+        if (s_ovf) st->select_overflow = 1;
+        if (a.do_select && !s_ovf) {
+            const T xk = KO::dec((K)s_xk);
+            T xk1 = xk;
+            if (!st->clamp_last) xk1 = s_have1 ? KO::dec((K)s_xk1) : KO::dec((K)s_succ);
+            // numpy _lerp
+            const T g = (T)st->gamma;
+            const T diff = sub_rn(xk1, xk);
+            T out = add_rn(xk, mul_rn(diff, g));
+            if (g >= (T)0.5) out = sub_rn(xk1, mul_rn(diff, sub_rn((T)1, g)));
+            cut = (double)out;
+            if (out > (T)0) cut_applied = 1;          // utility.py:288
+        }
+        unsigned long long l0, l1, l2, nnz_in, nnz_new, cap_ovf, sel_ovf, fb;
+        if (a.xch) {
+            l0 = a.xch[kXSq0]; l1 = a.xch[kXSq1]; l2 = a.xch[kXSq2];
+            nnz_in = a.xch[kXNnzIn]; nnz_new = a.xch[kXNnzNew];
+            cap_ovf = a.xch[kXCapOvf]; sel_ovf = a.xch[kXSelOvf]; fb = a.xch[kXFallback];
+        } else {
+            l0 = st->sq_limb[0]; l1 = st->sq_limb[1]; l2 = st->sq_limb[2];
+            nnz_in = st->nnz_in; nnz_new = st->cursor;
+            cap_ovf = (unsigned long long)st->capacity_overflow; sel_ovf = 0; fb = st->fb_count;
+        }
+        if (sel_ovf) st->select_overflow = 1;
+        if (cap_ovf) st->capacity_overflow = 1;
+        const double sumsq = ((double)l0 * 0x1p-64 + (double)l1 * 0x1p-32) + (double)l2;
+        const double delta = sqrt(sumsq);
+        const int step = st->step;
+        int done = 0, reason = CRWR_STOP_RUNNING;
+        if (delta < st->tol) {                        // utility.py:293
+            done = 1; reason = CRWR_STOP_TOLERANCE;
+        } else {
+            if (fabs(delta - st->delta_prev) < 0.001) st->plateau += 1;       // utility.py:298
+            st->delta_prev = delta;                                           // utility.py:301
+            if (st->plateau == 5) { done = 1; reason = CRWR_STOP_PLATEAU; }   // utility.py:302
+        }
+        if (step < kMaxTrace) {
+            crwr_step_record rec;
+            rec.nnz_in = (long long)nnz_in;
+            rec.nnz_new = (long long)nnz_new;
+            rec.cut = cut;
+            rec.delta = delta;
+            rec.cut_applied = cut_applied;
+            rec.plateau_hits = st->plateau;
+            a.trace[step] = rec;
+        }
+        st->last_delta = delta;
+        st->cut_on = cut_applied;
+        if (cut_applied) st->cut = cut;
+        st->parity ^= 1;
+        st->step = step + 1;
+        if (!done && step + 1 >= st->max_steps) { done = 1; reason = CRWR_STOP_MAX_STEPS; }
+        if (st->capacity_overflow || st->select_overflow) done = 1;
+        st->done = done;
+        st->stop_reason = reason;
+        st->last_fallback_rows = (int)fb;
+        st->last_max_kept = st->max_kept;
+        st->max_kept = 0;
+        if (!done) {
+            // counters of the next step (when stopping, cursor/max_row_len keep describing the result)
+            st->cursor = 0;
+            st->max_row_len = 0;
+        }
+        st->nnz_in = 0;
+        st->row_counter = 0;
+        st->fb_counter = 0;
+        st->fb_count = 0;
+        st->below = 0;
+        st->prefix = 0;
+        st->sq_limb[0] = 0; st->sq_limb[1] = 0; st->sq_limb[2] = 0;
+        a.own_block[0] = 0;
+        a.own_block[1] = ~0ull;
+    }
+    __syncthreads();   // thread 0 has consumed the exchanged counters
+    for (int i = t; i < kSelectLevels * kSelectBins + kXExtras; i += blockDim.x) a.hist[i] = 0ull;
+}
+
+// Sharded walk: publish this rank's step counters behind the level-0 histogram so that ONE
+// all-reduce (uint64 SUM) carries histogram, counts and the fixed-point delta^2.
+__global__ void pack_exchange_kernel(WalkState* st, unsigned long long* extras) {
+    if (st->done) return;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        extras[kXSq0] = st->sq_limb[0];
+        extras[kXSq1] = st->sq_limb[1];
+        extras[kXSq2] = st->sq_limb[2];
+        extras[kXNnzIn] = st->nnz_in;
+        extras[kXNnzNew] = st->cursor;
+        extras[kXCapOvf] = (unsigned long long)st->capacity_overflow;
+        extras[kXSelOvf] = (unsigned long long)st->select_overflow;
+        extras[kXFallback] = st->fb_count;
+    }
+}
+
+}  // namespace crwr

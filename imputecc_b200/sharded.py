@@ -1,0 +1,203 @@
+"""Sharded CRWR walk: restart rows split over the GPUs of one box.
+
+Rows of the iterate never interact inside a step, so each rank walks a contiguous block of
+restart rows against a replicated transition matrix.  The only coupled quantities are the
+global percentile cut and ||dQ||_F; both travel as small uint64 buffers:
+
+  exchange 0  all-reduce SUM   [8 counters incl. fixed-point delta^2 | level-0 histogram (4096)]
+  exchange 1  all-reduce SUM   level-1 histogram (4096)
+  exchange 2  all-gather       candidate block [count, successor key, <= 8192 keys]
+
+after which every rank derives the same cut and the same stop decision on its own device - no
+broadcast.  The collectives are torch.distributed calls (NCCL over NVLink on the GPU box, gloo
+in the CPU tests) on views of the library's workspace.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from .crwr import (DEFAULT_MAX_STEPS, DEFAULT_TOL, WalkInfo, Walker, markers_first_order, shard_rows, stack_row_blocks,
+                   symmetrise_device, validate_inputs, _require_cuda, _torch)
+
+
+class CudaPhases:
+    """The per-step phases of one shard, executed by libcrwr_b200 on this rank's GPU."""
+
+    def __init__(self, walker: Walker):
+        torch = _torch()
+        self.w = walker
+        lib, h = walker.lib, walker.handle
+        self.views = []
+        for which in range(3):
+            ptr = lib.crwr_exchange_ptr(h, which)
+            nbytes = int(lib.crwr_exchange_bytes(h, which))
+            self.views.append(walker._ws_view(int(ptr), nbytes, torch.int64))
+
+    def exchange(self, which):
+        return self.views[which]
+
+    def propagate(self):
+        _lib.check(self.w.lib.crwr_step_propagate(self.w.handle, self.w._stream()))
+
+    def hist(self, level):
+        _lib.check(self.w.lib.crwr_step_hist(self.w.handle, level, self.w._stream()))
+
+    def scan(self, level):
+        _lib.check(self.w.lib.crwr_step_scan(self.w.handle, level, self.w._stream()))
+
+    def gather(self):
+        _lib.check(self.w.lib.crwr_step_gather(self.w.handle, self.w._stream()))
+
+    def finish(self, gathered):
+        ptr = C.c_void_p(gathered.data_ptr()) if gathered is not None else C.c_void_p(0)
+        _lib.check(self.w.lib.crwr_step_finish(self.w.handle, ptr, self.w._stream()))
+
+    def set_variant(self, v):
+        _lib.check(self.w.lib.crwr_set_variant(self.w.handle, v))
+
+    def poll(self):
+        return self.w.poll()
+
+    def next_variant(self, st, variant, perc, issued):
+        return self.w._next_variant(st, variant, perc, issued)
+
+
+def _all_gather_blocks(dist, block, world, group):
+    torch = _torch()
+    out = torch.empty(world * block.numel(), dtype=block.dtype, device=block.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, block, group=group)
+    else:
+        parts = [out[r * block.numel():(r + 1) * block.numel()] for r in range(world)]
+        dist.all_gather(parts, block, group=group)
+    return out
+
+
+class TorchComm:
+    """The three collectives of a sharded step over a torch.distributed process group."""
+
+    def __init__(self, dist, group):
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, group=self.group)
+
+    def all_gather(self, block):
+        return _all_gather_blocks(self.dist, block, self.world, self.group)
+
+    def max_int(self, value: int, like) -> int:
+        torch = _torch()
+        v = torch.tensor([value], dtype=torch.int64, device=like.device)
+        self.dist.all_reduce(v, op=self.dist.ReduceOp.MAX, group=self.group)
+        return int(v.item())
+
+
+def run_sharded_walk(phases, comm, perc, max_steps):
+    """Drive utility.py:281-304 across the shards behind ``comm``; every rank issues the same sequence.
+
+    ``phases`` is a CudaPhases (the CPU tests pass an object with the same methods)."""
+    issued = 0
+    variant = 0
+    while True:
+        chunk = 1 if issued < 4 else 4
+        chunk = min(chunk, max_steps - issued)
+        phases.set_variant(variant)
+        for _ in range(chunk):
+            phases.propagate()
+            if issued >= 1:
+                phases.hist(0)
+            comm.all_reduce_sum(phases.exchange(0))
+            if issued >= 1:
+                phases.scan(0)
+                phases.hist(1)
+                comm.all_reduce_sum(phases.exchange(1))
+                phases.scan(1)
+                phases.gather()
+                phases.finish(comm.all_gather(phases.exchange(2)))
+            else:
+                phases.finish(None)
+            issued += 1
+        st = phases.poll()
+        if st.stop_reason != 0 or issued >= max_steps:
+            return st
+        # the size class affects speed only, never results; keep the shards in lockstep anyway
+        variant = comm.max_int(phases.next_variant(st, variant, perc, issued), phases.exchange(0))
+
+
+def gather_row_blocks(dist, group, ip, ix, dt, rows_of_rank, m):
+    """All-gather per-rank CSR row blocks (device tensors) into one m x m CSR on every rank."""
+    torch = _torch()
+    world = dist.get_world_size(group)
+    dev = dt.device
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    counts[dist.get_rank(group)] = ix.numel()
+    dist.all_reduce(counts, group=group)
+    counts_h = [int(c) for c in counts.cpu()]
+    pad = max(max(counts_h), 1)
+    max_rows = max(r1 - r0 for r0, r1 in rows_of_rank)
+
+    def padded(t, n, dtype):
+        out = torch.zeros(n, dtype=dtype, device=dev)
+        out[:t.numel()] = t
+        return out
+
+    g_ix = _all_gather_blocks(dist, padded(ix, pad, torch.int32), world, group)
+    g_dt = _all_gather_blocks(dist, padded(dt, pad, dt.dtype), world, group)
+    g_ip = _all_gather_blocks(dist, padded(ip, max_rows + 1, torch.int64), world, group)
+    ips, ixs, dts = [], [], []
+    base = 0
+    for r, (r0, r1) in enumerate(rows_of_rank):
+        rows = r1 - r0
+        rip = g_ip[r * (max_rows + 1): r * (max_rows + 1) + rows + 1]
+        ips.append(rip[:-1] + base)
+        ixs.append(g_ix[r * pad: r * pad + counts_h[r]])
+        dts.append(g_dt[r * pad: r * pad + counts_h[r]])
+        base += counts_h[r]
+    full_ip = torch.cat(ips + [torch.tensor([base], dtype=torch.int64, device=dev)])
+    return full_ip, torch.cat(ixs), torch.cat(dts)
+
+
+def crwr_impute_sharded(normcc, marker_idx_sorted, rp, perc, tol=DEFAULT_TOL, max_steps=DEFAULT_MAX_STEPS,
+                        dtype=np.float32, device=None, return_info=False, group=None):
+    """crwr_impute with the restart rows sharded over the ranks of ``group`` (default: WORLD).
+
+    Every rank passes the same inputs and receives the same imputed matrix."""
+    torch = _torch()
+    import torch.distributed as dist
+    validate_inputs(normcc, marker_idx_sorted, rp, perc)
+    if group is None:
+        group = dist.group.WORLD
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    device = _require_cuda(device)
+    M = sp.csr_matrix(normcc)
+    if not M.has_canonical_format:
+        M = M.copy()
+        M.sum_duplicates()
+    idx = np.asarray(marker_idx_sorted, dtype=np.int64)
+    n, m = M.shape[0], idx.size
+    if world > m:
+        raise ValueError("more ranks than restart rows")
+    new_of_old = markers_first_order(n, idx)
+    ranges = shard_rows(m, world, weights=np.diff(M.indptr)[idx])
+    r0, r1 = ranges[rank]
+    w = Walker(n, m, dtype=dtype, device=device, transition_nnz_cap=int(M.nnz) + n, row_range=(r0, r1), n_shards=world)
+    try:
+        nnz_p = w.build_transition(M.indptr, M.indices, M.data, new_of_old)
+        with torch.cuda.device(device):
+            w.walk_init(rp, perc, tol, max_steps)
+            st = run_sharded_walk(CudaPhases(w), TorchComm(dist, group), perc, max_steps)
+            ip, ix, dt = w.result_device()
+            f_ip, f_ix, f_dt = gather_row_blocks(dist, group, ip, ix, dt, ranges, m)
+            e_ip, e_ix, e_dt = symmetrise_device(f_ip, f_ix, f_dt, m)
+        E = sp.csr_matrix((e_dt.cpu().numpy(), e_ix.cpu().numpy(), e_ip.cpu().numpy()), shape=(m, m))
+        info = WalkInfo(int(st.steps_done), _lib.STOP_NAMES.get(int(st.stop_reason), "?"), w.trace() if return_info else [],
+                        nnz_p, w.regrows)
+    finally:
+        w.close()
+    return (E, info) if return_info else E

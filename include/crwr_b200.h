@@ -1,0 +1,174 @@
+/*
+ * crwr_b200.h - C ABI of libcrwr_b200.so: constrained random walk with restart (CRWR)
+ * imputation on NVIDIA B200 (sm_100a).
+ *
+ * The reference (dyxstat/ImputeCC, pure Python) has no FFI for this path; its boundary is two
+ * Python functions.  The entry points below are what a binding of that boundary needs:
+ *
+ *   reference interface                                   replaced by
+ *   ----------------------------------------------------  ------------------------------------
+ *   Script/imputation.py:112-119  permute + strip diag +  crwr_build_transition
+ *                                 self-loops + row scale
+ *   Script/utility.py:270-279     random_walk_cpu entry,  crwr_set_transition (caller-built P),
+ *                                 restart matrix I, Q=I   crwr_walk_init
+ *   Script/utility.py:281-304     the walk loop           crwr_walk_enqueue / crwr_walk_poll
+ *                                                         (per-phase calls for the sharded walk)
+ *   Script/utility.py:306-307     Q[:m,:m]                crwr_result_count / crwr_result_write
+ *   Script/imputation.py:122-127  E=Q+Q^T, D^-1/2 E D^-1/2 crwr_symmetrise_count / _write
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer (e.g. torch.Tensor.data_ptr()); h_* is host.
+ *   - the library never allocates device memory: the caller passes one workspace block whose
+ *     size crwr_workspace_bytes() reports, plus explicit output buffers (two-call pattern:
+ *     *_count then *_write, because output sizes are data dependent).
+ *   - stream is a cudaStream_t passed as void*; calls only enqueue work unless stated.
+ *   - return value: 0 = CRWR_OK, negative = error; crwr_last_error() gives the message
+ *     (thread-local).  There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef CRWR_B200_H
+#define CRWR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRWR_ABI_VERSION 1
+#define CRWR_SHARD_CAND 8192   /* percentile candidates one shard may contribute per step */
+
+enum { CRWR_F32 = 0, CRWR_F64 = 1 };
+
+enum {
+    CRWR_OK = 0,
+    CRWR_ERR_INVALID = -1,     /* bad argument */
+    CRWR_ERR_CUDA = -2,        /* CUDA runtime error */
+    CRWR_ERR_CAPACITY = -3,    /* iterate buffers too small: recreate with a larger capacity */
+    CRWR_ERR_STATE = -4        /* call out of order */
+};
+
+enum { CRWR_STOP_RUNNING = 0, CRWR_STOP_TOLERANCE = 1, CRWR_STOP_PLATEAU = 2, CRWR_STOP_MAX_STEPS = 3 };
+
+typedef struct crwr_handle_s* crwr_handle;
+
+typedef struct crwr_config {
+    int32_t dtype;              /* CRWR_F32 (reference arithmetic, imputation.py:119) or CRWR_F64 */
+    int32_t device;             /* CUDA device ordinal */
+    int64_t n_contigs;          /* N: order of the contact matrix */
+    int64_t n_markers;          /* m: restart rows of the whole job (utility.py:274) */
+    int64_t row_begin;          /* this shard walks restart rows [row_begin, row_end) */
+    int64_t row_end;
+    int64_t transition_nnz_cap; /* capacity for nnz(P) */
+    int64_t iterate_cap;        /* capacity, in entries, of EACH of the two iterate buffers */
+    int32_t n_shards;           /* ranks sharing the walk (1 = unsharded: rows must be [0, m)) */
+    int32_t reserved;
+} crwr_config;
+
+/* One record per walk step; mirrors oracle StepTrace. */
+typedef struct crwr_step_record {
+    int64_t nnz_in;     /* entries of the thresholded iterate entering the step */
+    int64_t nnz_new;    /* entries of (1-rp) Q P + rp I */
+    double cut;         /* percentile value; NaN when no cut was computed (step 0) */
+    double delta;       /* ||Q_prev - Q_new||_F */
+    int32_t cut_applied;
+    int32_t plateau_hits;
+} crwr_step_record;
+
+typedef struct crwr_status {
+    int32_t steps_done;
+    int32_t stop_reason;        /* CRWR_STOP_* */
+    int32_t capacity_overflow;  /* 1 = an iterate buffer overflowed; results invalid */
+    int32_t fallback_rows;      /* rows that took the large-row path in the last step */
+    int64_t nnz_iterate;        /* entries currently stored (before the last cut) */
+    int64_t max_row_len;        /* longest stored row */
+    int64_t max_kept;           /* longest kept (post-cut) operand row read by the last step */
+    double last_cut;
+    double last_delta;
+} crwr_status;
+
+int32_t crwr_abi_version(void);
+const char* crwr_last_error(void);
+
+/* Bytes of device workspace crwr_create needs for this configuration. */
+int64_t crwr_workspace_bytes(const crwr_config* cfg);
+
+int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace, int64_t workspace_bytes);
+int32_t crwr_destroy(crwr_handle h);
+
+/* imputation.py:112-119.  NormCC CSR (int64 indptr, int32 indices, float64 data) in ORIGINAL
+ * contig order plus d_new_of_old[N] (position of each contig in the markers-first order of
+ * imputation.py:98-110).  Builds P (CSR, markers-first index space, sorted rows) in the
+ * workspace.  h_nnz_out (optional, host) receives nnz(P) after an internal stream sync. */
+int32_t crwr_build_transition(crwr_handle h, const int64_t* d_indptr, const int32_t* d_indices,
+                              const double* d_data, int64_t nnz, const int32_t* d_new_of_old,
+                              int64_t* h_nnz_out, void* stream);
+
+/* B-inner (utility.py:270): caller supplies P exactly as random_walk_cpu would receive it
+ * (CSR, int32 indptr/indices, values of the handle's dtype, markers in rows/cols 0..m-1). */
+int32_t crwr_set_transition(crwr_handle h, const int32_t* d_indptr, const int32_t* d_indices,
+                            const void* d_data, int64_t nnz, void* stream);
+
+/* Copy P out (for tests): arrays sized N+1 / nnz / nnz. */
+int32_t crwr_get_transition(crwr_handle h, int32_t* d_indptr, int32_t* d_indices, void* d_data, void* stream);
+
+/* utility.py:275-280: Q = I, counters cleared.  perc in [0,100]; tol 0.01 and max_steps 500 in
+ * the reference (imputation.py:120, utility.py:281). */
+int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_t max_steps, void* stream);
+
+/* Hash-table size class of the propagation kernel (0..3: 1024/2048/4096/8192 accumulator slots per
+ * restart row); rows that do not fit take the large-row path.  Host policy picks it from
+ * crwr_status.max_row_len / fallback_rows. */
+int32_t crwr_set_variant(crwr_handle h, int32_t variant);
+int64_t crwr_transition_nnz(crwr_handle h);
+
+/* Enqueue up to n_steps walk steps (utility.py:282-304).  Stop rules are evaluated on the
+ * device; steps enqueued after the walk has stopped are no-ops.  Single-shard walks only. */
+int32_t crwr_walk_enqueue(crwr_handle h, int32_t n_steps, void* stream);
+
+/* Sharded walk (one process per GPU, rows [row_begin,row_end) each).  One step is
+ *   propagate; hist(0); ALLREDUCE-SUM-u64 exchange 0; scan(0); hist(1); ALLREDUCE exchange 1;
+ *   scan(1); gather; ALLGATHER exchange 2 (candidate block); finish(gathered blocks)
+ * Step 0 has no cut (utility.py:286): propagate; ALLREDUCE exchange 0; finish(NULL).
+ * Exchange 0 = [8 counters incl. the fixed-point delta^2 | level-0 histogram], exchange 1 =
+ * level-1 histogram, exchange 2 = [count, successor key, CRWR_SHARD_CAND keys] (all uint64).
+ * Every rank then derives the identical cut and stop decision.  See INTEGRATION.md. */
+int32_t crwr_step_propagate(crwr_handle h, void* stream);
+int32_t crwr_step_hist(crwr_handle h, int32_t level, void* stream);
+int32_t crwr_step_scan(crwr_handle h, int32_t level, void* stream);
+int32_t crwr_step_gather(crwr_handle h, void* stream);
+int32_t crwr_step_finish(crwr_handle h, const void* d_gathered_blocks, void* stream);
+void* crwr_exchange_ptr(crwr_handle h, int32_t which);     /* device pointer inside the workspace */
+int64_t crwr_exchange_bytes(crwr_handle h, int32_t which);
+
+/* Synchronises the stream and fills *h_out. */
+int32_t crwr_walk_poll(crwr_handle h, crwr_status* h_out, void* stream);
+/* Copies the per-step records (steps_done of them, at most cap) to host; syncs. */
+int32_t crwr_walk_trace(crwr_handle h, crwr_step_record* h_out, int32_t cap, void* stream);
+
+/* utility.py:306-307: the columns < m of the final (cut) iterate, rows of this shard.
+ * count: syncs and returns the number of entries in *h_nnz.  write: CSR with int64 indptr
+ * (rows_local+1), int32 indices, values of the handle's dtype; columns ascending per row. */
+int32_t crwr_result_count(crwr_handle h, int64_t* h_nnz, void* stream);
+int32_t crwr_result_write(crwr_handle h, int64_t* d_indptr, int32_t* d_indices, void* d_data, void* stream);
+/* The whole m_local x N iterate after the last cut (for tests / checkpoints). */
+int32_t crwr_iterate_count(crwr_handle h, int64_t* h_nnz, void* stream);
+int32_t crwr_iterate_write(crwr_handle h, int64_t* d_indptr, int32_t* d_indices, void* d_data, void* stream);
+
+/* imputation.py:122-127 on an m x m CSR matrix Q (sorted rows): E = Q + Q^T, d = colsum(E),
+ * d[d==0] = 1, E = D^-1/2 E D^-1/2.  Stateless apart from the scratch block the caller passes
+ * (crwr_symmetrise_scratch_bytes).  count syncs; write emits CSR with sorted rows. */
+int64_t crwr_symmetrise_scratch_bytes(int64_t m, int64_t nnz);
+int32_t crwr_symmetrise_count(int32_t dtype, int64_t m, const int64_t* d_indptr, const int32_t* d_indices,
+                              const void* d_data, int64_t nnz, void* d_scratch, int64_t scratch_bytes,
+                              int64_t* h_nnz_out, void* stream);
+int32_t crwr_symmetrise_write(int32_t dtype, int64_t m, const int64_t* d_indptr, const int32_t* d_indices,
+                              const void* d_data, int64_t nnz, void* d_scratch, int64_t scratch_bytes,
+                              int64_t* d_out_indptr, int32_t* d_out_indices, void* d_out_data, void* stream);
+
+/* Launch counter: kernels this library launched since the last reset (bench gpu_launches). */
+int64_t crwr_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRWR_B200_H */

@@ -1,0 +1,255 @@
+"""GPU parity tests: the CUDA path, called through the public API / C ABI, against the oracle and
+the golden vectors produced by the unmodified reference (tests/golden, oracle/make_golden.py).
+
+Gates (north_star): float64 walk - identical support, values within rel 1e-6 of the reference's
+float64 run; float32 walk (the reference's own arithmetic) - same gate against the reference's
+float32 run.  Because the kernels keep scipy's summation order, both are in fact expected to be
+BIT-identical; `test_bit_identity_*` pins that stronger property separately.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import golden_names, load_csr, load_golden, same_support
+from oracle import crwr_oracle as oracle
+import imputecc_b200 as pkg
+from imputecc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-6        # north_star: "matches the reference within rel 1e-6"
+
+
+def _canon(A):
+    A = sp.csr_matrix(A).copy()
+    A.sort_indices()
+    return A
+
+
+def _assert_close(got, want, what):
+    got, want = _canon(got), _canon(want)
+    assert got.shape == want.shape, what
+    assert same_support(got, want), "%s: support differs (nnz %d vs %d)" % (what, got.nnz, want.nnz)
+    if want.nnz:
+        rel = np.abs(got.data.astype(np.float64) - want.data.astype(np.float64)) / np.abs(want.data.astype(np.float64))
+        assert rel.max() <= REL_TOL, "%s: max rel err %.3e" % (what, rel.max())
+
+
+def _bit_equal(got, want):
+    got, want = _canon(got), _canon(want)
+    return same_support(got, want) and got.dtype == want.dtype and np.array_equal(got.data, want.data)
+
+
+def _P_from_golden(rec, dtype):
+    normcc = load_csr(rec, "normcc")
+    perm = oracle.marker_permutation(normcc.shape[0], rec["marker_idx"])
+    return oracle.transition_matrix(normcc, perm, np.float32).astype(dtype)     # as make_golden fed it
+
+
+# ---------------------------------------------------------------------------------------------
+# K1: transition matrix
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["bundled_m120_t80_rp50", "synth1500_t80_rp50", "synth3000dense_t80_rp50", "asym400_t60_rp50"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_transition_matrix(cuda_device, name, dtype):
+    rec = load_golden(name)
+    normcc = load_csr(rec, "normcc")
+    idx = rec["marker_idx"]
+    w = pkg.Walker(normcc.shape[0], len(idx), dtype=dtype, device=cuda_device, transition_nnz_cap=normcc.nnz + normcc.shape[0])
+    try:
+        w.build_transition(normcc.indptr, normcc.indices, normcc.data, pkg.markers_first_order(normcc.shape[0], idx))
+        P = w.transition()
+    finally:
+        w.close()
+    want = oracle.transition_matrix(normcc, oracle.marker_permutation(normcc.shape[0], idx), dtype)
+    assert P.dtype == dtype and P.has_sorted_indices
+    assert _bit_equal(P, want)
+    if dtype == np.float32:
+        assert _bit_equal(P, load_csr(rec, "P32"))
+
+
+# ---------------------------------------------------------------------------------------------
+# B-inner: random_walk_b200 == random_walk_cpu
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("tag,dtype", [("64", np.float64), ("32", np.float32)])
+def test_walk_matches_reference(cuda_device, name, tag, dtype):
+    rec = load_golden(name)
+    P = _P_from_golden(rec, dtype)
+    m = len(rec["marker_idx"])
+    Q, info = pkg.random_walk_b200(P, float(rec["rp"]), int(rec["perc"]), 0.01, m, device=cuda_device, return_info=True)
+    want = load_csr(rec, "walk" + tag)
+    assert Q.format == "csc" and Q.dtype == dtype and Q.shape == (m, m)
+    # per-step trace against the oracle first: it localises a failure to a step
+    tr = oracle.WalkTrace()
+    oracle.crwr_walk(P, float(rec["rp"]), int(rec["perc"]), 0.01, m, trace=tr)
+    got_steps = [(t["nnz_in"], t["nnz_new"]) for t in info.trace]
+    want_steps = [(t.nnz_in, t.nnz_new) for t in tr.steps]
+    assert got_steps == want_steps, "trace diverges: %r vs %r" % (got_steps[:6], want_steps[:6])
+    assert info.stop_reason == tr.stop_reason
+    for g, t in zip(info.trace, tr.steps):
+        assert abs(g["delta"] - t.delta) <= 1e-5 * max(1.0, t.delta)
+        if t.step >= 1:
+            assert g["cut"] == pytest.approx(t.cut, rel=1e-6)
+    _assert_close(Q, want, name + "/walk" + tag)
+
+
+@pytest.mark.parametrize("name", ["bundled_m120_t80_rp50", "bundled_m250_t50_rp50", "synth1500_t80_rp50", "synth1500_t50_rp30",
+                                  "synth3000dense_t80_rp50", "asym400_t60_rp50", "bundled_m120_t80_rp30"])
+@pytest.mark.parametrize("tag,dtype", [("64", np.float64), ("32", np.float32)])
+def test_bit_identity_with_reference_walk(cuda_device, name, tag, dtype):
+    rec = load_golden(name)
+    P = _P_from_golden(rec, dtype)
+    Q = pkg.random_walk_b200(P, float(rec["rp"]), int(rec["perc"]), 0.01, len(rec["marker_idx"]), device=cuda_device)
+    assert _bit_equal(Q, load_csr(rec, "walk" + tag))
+
+
+# ---------------------------------------------------------------------------------------------
+# B-outer: crwr_impute == ImputeMatrix._imputation
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_impute_matches_reference_float32(cuda_device, name):
+    rec = load_golden(name)
+    normcc = load_csr(rec, "normcc")
+    E = pkg.crwr_impute(normcc, rec["marker_idx"], float(rec["rp"]), int(rec["perc"]), dtype=np.float32, device=cuda_device)
+    assert E.dtype == np.float32
+    _assert_close(E, load_csr(rec, "E32"), name + "/E32")
+
+
+@pytest.mark.parametrize("name", ["bundled_m120_t80_rp50", "synth1500_t80_rp50", "synth3000dense_t80_rp50", "asym400_t60_rp50"])
+def test_impute_float64_matches_oracle(cuda_device, name):
+    rec = load_golden(name)
+    normcc = load_csr(rec, "normcc")
+    E = pkg.crwr_impute(normcc, rec["marker_idx"], float(rec["rp"]), int(rec["perc"]), dtype=np.float64, device=cuda_device)
+    want = oracle.crwr_impute(normcc, rec["marker_idx"], float(rec["rp"]), int(rec["perc"]), dtype=np.float64)
+    _assert_close(E, want, name + "/E64")
+
+
+def test_symmetrise_normalise_bit_identical(cuda_device):
+    rng = np.random.default_rng(0)
+    for dtype in (np.float32, np.float64):
+        Q = sp.random(300, 300, density=0.05, random_state=rng, format="csr").astype(dtype)
+        Q.data = (Q.data + dtype(0.01)).astype(dtype)
+        Q[5, :] = 0; Q[:, 5] = 0; Q.eliminate_zeros()            # an empty row/column: d == 0 -> 1
+        got = pkg.symmetrise_normalise(Q, device=cuda_device)
+        want = oracle.symmetrise_normalise(Q.tocsc())
+        assert _bit_equal(got, want)
+
+
+def test_drop_in_for_ImputeMatrix(cuda_device):
+    """imputation_b200 reads the same attributes and returns the same tuple as _imputation."""
+    rec = load_golden("bundled_m120_t80_rp50")
+    normcc = load_csr(rec, "normcc")
+    n = normcc.shape[0]
+
+    class Obj:
+        pass
+    o = Obj()
+    names = np.array(["ctg%06d" % i for i in range(n)], dtype=object)
+    o.contig_info = np.stack([names, np.zeros(n, dtype=object), np.ones(n, dtype=object)], axis=1)
+    o.dict_contigRev = {nm: i for i, nm in enumerate(names)}
+    o.normcc_matrix = normcc
+    o.contig_markers = {names[i]: ["g"] for i in rec["marker_idx"][::-1]}       # any dict order
+    o.rwr_rp, o.rwr_perc = 0.5, 80
+    local, rev, E = pkg.imputation_b200(o, device=cuda_device)
+    assert sp.isspmatrix_lil(E) and E.dtype == np.float32
+    assert list(local[:, 0]) == list(names[rec["marker_idx"]])
+    assert rev[names[rec["marker_idx"][3]]] == 3
+    _assert_close(E.tocsr(), load_csr(rec, "E32"), "drop-in E")
+    import pickle
+    assert pickle.loads(pickle.dumps(E)).nnz == E.nnz                           # ImputeCC.py:241 pickles the result
+
+
+# ---------------------------------------------------------------------------------------------
+# larger live-oracle cases and size-independent properties
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_c2_sized_walk_against_live_oracle(cuda_device, dtype):
+    M, idx = synth.make_workload(synth.Workload("c2ish", 6000, 960, 100, 16))
+    E, info = pkg.crwr_impute(M, idx, 0.5, 80, dtype=dtype, device=cuda_device, return_info=True)
+    tr = oracle.WalkTrace()
+    want = oracle.crwr_impute(M, idx, 0.5, 80, dtype=dtype, trace=tr)
+    assert info.steps == len(tr.steps) and info.stop_reason == tr.stop_reason
+    assert [t["nnz_new"] for t in info.trace] == [t.nnz_new for t in tr.steps]
+    _assert_close(E, want, "c2ish")
+    Es = sp.csr_matrix(E)
+    assert (abs(Es - Es.T) > 0).nnz == 0                                        # E is exactly symmetric
+
+
+def test_result_is_independent_of_kernel_size_class_and_large_row_path(cuda_device):
+    """Hash-table variants and the dense large-row kernel must agree bit for bit."""
+    rec = load_golden("synth3000dense_t80_rp50")
+    P = _P_from_golden(rec, np.float64)
+    m = len(rec["marker_idx"])
+    outs = []
+    for variant in (0, 1, 2, 3):
+        w = pkg.Walker(P.shape[0], m, dtype=np.float64, device=cuda_device, transition_nnz_cap=P.nnz)
+        try:
+            w.set_transition(P)
+            w._next_variant = lambda st, v, perc, issued, _v=variant: _v        # pin the size class
+            st = w.walk(0.5, 80)
+            outs.append((int(st.steps_done), w.iterate()))
+        finally:
+            w.close()
+    for steps, it in outs[1:]:
+        assert steps == outs[0][0]
+        assert _bit_equal(it, outs[0][1])
+
+
+def test_iterate_rows_sum_below_one_and_restart_present(cuda_device):
+    """Properties that hold at any size: rows of the kept iterate are sub-stochastic for a symmetric
+    input, and every value exceeds the last cut."""
+    M, idx = synth.make_workload(synth.Workload("p", 4000, 640, 100, 16))
+    n, m = M.shape[0], idx.size
+    w = pkg.Walker(n, m, dtype=np.float64, device=cuda_device, transition_nnz_cap=M.nnz + n)
+    try:
+        w.build_transition(M.indptr, M.indices, M.data, pkg.markers_first_order(n, idx))
+        P = w.transition()
+        assert np.allclose(np.asarray(P.sum(axis=1)).ravel(), 1.0, atol=1e-12)   # symmetric input: row-stochastic
+        st = w.walk(0.5, 80)
+        it = w.iterate()
+        assert it.shape == (m, n)
+        assert np.all(np.asarray(it.sum(axis=1)).ravel() <= 1.0 + 1e-9)
+        assert it.data.min() > st.last_cut
+        tr = w.trace()
+        assert tr[-1]["nnz_new"] >= it.nnz and len(tr) == st.steps_done
+    finally:
+        w.close()
+
+
+def test_empty_result_and_edge_percentiles(cuda_device):
+    rec = load_golden("bundled_m120_t95_rp50")
+    E = pkg.crwr_impute(load_csr(rec, "normcc"), rec["marker_idx"], 0.5, 95, device=cuda_device)
+    assert E.nnz == 0 and E.shape == (120, 120)                                 # pre_clustering.py:47 branches on this
+    M = synth.contact_matrix(300, 30, 8, 1, seed=9)
+    one = pkg.crwr_impute(M, np.array([17]), 0.5, 80, device=cuda_device)      # m = 1
+    assert one.shape == (1, 1)
+    want = oracle.crwr_impute(M, np.array([17]), 0.5, 80)
+    _assert_close(one, want, "m=1")
+
+
+def test_argument_errors(cuda_device):
+    M = synth.contact_matrix(300, 30, 8, 1, seed=9)
+    with pytest.raises(ValueError):
+        pkg.crwr_impute(M, np.array([], dtype=int), 0.5, 80, device=cuda_device)
+    with pytest.raises(ValueError):
+        pkg.crwr_impute(M, np.array([3, 2]), 0.5, 80, device=cuda_device)
+    with pytest.raises(ValueError):
+        pkg.crwr_impute(M, np.array([3]), 0.5, 180, device=cuda_device)
+    with pytest.raises(ValueError):
+        pkg.random_walk_b200(M.astype(np.float32), 0.5, 80, 0.01, 0, device=cuda_device)
+
+
+def test_capacity_regrow(cuda_device):
+    """An undersized iterate buffer is detected on the device and the walk restarts larger."""
+    rec = load_golden("synth1500_t50_rp30")
+    P = _P_from_golden(rec, np.float32)
+    m = len(rec["marker_idx"])
+    w = pkg.Walker(P.shape[0], m, dtype=np.float32, device=cuda_device, transition_nnz_cap=P.nnz, iterate_cap=4 * m)
+    try:
+        w.set_transition(P)
+        w.walk(0.3, 50)
+        assert w.regrows >= 1
+        assert _bit_equal(w.result().tocsc(), load_csr(rec, "walk32"))
+    finally:
+        w.close()
