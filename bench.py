@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py - CRWR imputation throughput on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3_sparse] [--dtype f32|f64]
+    python bench.py --impl reference ...      # the reference's scipy algorithm on the host cores
+
+One bench "step" = one complete CRWR imputation (normalise -> walk to its stop rule -> slice ->
+symmetrise) of the named synthetic workload; the metric is BASELINE.json's "CRWR walk-steps/s":
+walk steps executed per second of walk time.
+
+  value  device-resident: transition matrix already in HBM, timed region = the walk itself
+         (crwr_walk_init .. stop rule), CUDA events on the launching stream, max over ranks.
+  e2e    the same metric through the public call crwr_impute() with HOST buffers: pinned
+         NormCC CSR in, scipy matrix out, copies inside the timed region.
+  roofline  the dominant kernel (propagate_kernel): algorithmic bytes per launch / its mean
+         duration measured live with CUDA events, against MEASURED_PEAKS.json hbm_gbs.
+
+N > 1 (torchrun): weak scaling - every rank walks 8,000 restart rows of a problem N times larger
+(8,000 N markers on 50,000 N contigs, the m/N ratio of BASELINE configs 2-4); value is scaled by
+m/8000 so that it stays a whole-job aggregate.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+BLOCK_MARKERS = 8000
+
+
+def workload_for(name: str, world: int):
+    from imputecc_b200 import synth
+    base = synth.WORKLOADS[name]
+    if world == 1:
+        return base
+    return synth.Workload("%s_x%d" % (base.name, world), base.n_contigs * world, base.n_markers * world,
+                          base.genome_size, base.intra_degree, base.inter_degree, base.matrix_seed, base.marker_seed)
+
+
+def walk_bytes(trace, nnz_p, n, s):
+    """Algorithmic bytes of the walk (SURVEY.md §8d B_step) and the propagate kernel's share of it."""
+    total = prop = 0
+    for i, t in enumerate(trace):
+        kept = t.get("nnz_kept", t["nnz_new"])
+        w = nnz_p * (s + 4) + 4 * (n + 1)
+        p = w + (s + 4) * (t["nnz_in"] + t["nnz_new"])          # stream W, read kept operand, write product
+        total += p
+        if i >= 1:
+            total += (s + 4) * kept + s * t["nnz_new"]          # selection read + kept write
+        prop += p
+    return total, prop
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_hbm_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def pinned_csr(M):
+    """scipy CSR whose arrays live in pinned host memory (asynchronous H2D)."""
+    import scipy.sparse as sp
+    import torch
+    ip = torch.from_numpy(M.indptr.astype(np.int64)).pin_memory()
+    ix = torch.from_numpy(M.indices.astype(np.int32)).pin_memory()
+    dt = torch.from_numpy(M.data.astype(np.float64)).pin_memory()
+    P = sp.csr_matrix((dt.numpy(), ix.numpy(), ip.numpy()), shape=M.shape, copy=False)
+    P._pins = (ip, ix, dt)
+    return P
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own algorithm (scipy / numpy, single-threaded like the reference) on the host."""
+    if rank != 0:
+        return
+    from imputecc_b200 import synth
+    from oracle import crwr_oracle as oracle
+    wl = workload_for(args.workload, 1)
+    M, idx = synth.make_workload(wl)
+    np_dtype = np.float32               # the reference casts P to float32 (imputation.py:119)
+    perm = oracle.marker_permutation(M.shape[0], idx)
+    P = oracle.transition_matrix(M, perm, np_dtype)
+    max_steps = args.ref_walk_steps
+    times, steps = [], 0
+    for i in range(args.warmup + args.steps):
+        tr = oracle.WalkTrace()
+        t0 = time.perf_counter()
+        oracle.crwr_walk(P, 0.5, 80, 0.01, idx.size, max_steps=max_steps, trace=tr)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+            steps += len(tr.steps)
+    total = sum(times)
+    value = steps / total
+    sample = "full walk" if max_steps >= 500 else "first %d walk steps of each walk" % max_steps
+    line = {"impl": "reference", "metric": "crwr_walk_steps_per_s", "value": value, "unit": "walk-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(wl, 1, "f32"),
+            "cpu_baseline": {"value": value, "unit": "walk-steps/s", "cores": 1, "kind": "port",
+                             "sample": "%s; scipy.sparse + np.percentile are serial, 1 of %d host cores used" %
+                                       (sample, os.cpu_count())},
+            "e2e": {"value": value, "unit": "walk-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_dict(wl, world, dtype):
+    return {"workload": "%s: synthetic NormCC-like CSR, %d marker contigs on %d contigs, genome %d, intra-degree %d, "
+                        "rwr-rp 0.5, rwr-thres 80" % (wl.name, wl.n_markers, wl.n_contigs, wl.genome_size, wl.intra_degree),
+            "n_markers": wl.n_markers, "n_contigs": wl.n_contigs, "rp": 0.5, "perc": 80, "walk_dtype": dtype,
+            "parallelism": "restart rows sharded over %d GPU(s), transition matrix replicated" % world,
+            "l2": "L2 flushed (256 MiB write) between timed imputations"}
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("CRWR_BENCH_WORKLOAD", "c3_sparse"))
+    ap.add_argument("--dtype", default=os.environ.get("CRWR_BENCH_DTYPE", "f32"), choices=["f32", "f64"])
+    ap.add_argument("--ref-walk-steps", type=int, default=500, help="bound on walk steps per reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: imputecc_b200 has no CPU path (use --impl reference for the CPU arm)")
+    import imputecc_b200 as pkg
+    from imputecc_b200 import _lib, sharded, synth
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+    np_dtype = np.float64 if args.dtype == "f64" else np.float32
+    s = 8 if args.dtype == "f64" else 4
+
+    wl = workload_for(args.workload, world)
+    M, idx = synth.make_workload(wl)
+    n, m = M.shape[0], idx.size
+    new_of_old = pkg.markers_first_order(n, idx)
+    ranges = pkg.shard_rows(m, world, weights=np.diff(M.indptr)[idx])
+    walker = pkg.Walker(n, m, dtype=np_dtype, device=device, transition_nnz_cap=M.nnz + n,
+                        row_range=ranges[rank] if world > 1 else None, n_shards=world)
+    nnz_p = walker.build_transition(M.indptr, M.indices, M.data, new_of_old)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    comm = sharded.TorchComm(dist, dist.group.WORLD) if world > 1 else None
+
+    def one_walk():
+        if world == 1:
+            return walker.walk(0.5, 80)
+        walker.walk_init(0.5, 80)
+        return sharded.run_sharded_walk(sharded.CudaPhases(walker), comm, 80, 500)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    # ---- device-resident walk -------------------------------------------------------------
+    for _ in range(args.warmup):
+        one_walk()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.crwr_launch_count(1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    walk_steps = 0
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        st = one_walk()
+        b.record()
+        walk_steps += int(st.steps_done)
+    barrier()
+    launches = int(lib.crwr_launch_count(0))
+    walk_ms = sum(a.elapsed_time(b) for a, b in ev)
+    trace = walker.trace()
+
+    # ---- dominant kernel, live (CUDA events inside the library around each propagate launch) ----
+    lib.crwr_profile(walker.handle, 1)
+    flush.fill_(1)
+    one_walk()
+    tot_ms, n_launch = _lib.C.c_double(0), _lib.C.c_int64(0)
+    _lib.check(lib.crwr_profile_read(walker.handle, _lib.C.byref(tot_ms), _lib.C.byref(n_launch), walker._stream()))
+    lib.crwr_profile(walker.handle, 0)
+    steps_per_walk = len(trace)
+    prop_ms_per_launch = tot_ms.value / max(steps_per_walk, 1)       # launches after the stop are no-ops (~0 ms)
+
+    # ---- end to end through the public API, host buffers --------------------------------------
+    Mp = pinned_csr(M)
+    group = dist.group.WORLD if world > 1 else None
+    e2e_times, e2e_steps, d2h = [], 0, 0
+    for i in range(args.warmup + args.steps):
+        flush.fill_(1)
+        barrier()
+        t0 = time.perf_counter()
+        E, info = pkg.crwr_impute(Mp, idx, 0.5, 80, dtype=np_dtype, device=device, return_info=False, group=group), None
+        torch.cuda.synchronize(device)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            e2e_times.append(dt)
+            e2e_steps += steps_per_walk
+            d2h = E.data.nbytes + E.indices.nbytes + 8 * (m + 1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- reduce over ranks (max time) -----------------------------------------------------------
+    t = torch.tensor([walk_ms, sum(e2e_times) * 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    walk_ms, e2e_ms = float(t[0]), float(t[1])
+
+    scale = m / BLOCK_MARKERS if world > 1 else 1.0
+    value = scale * walk_steps / (walk_ms * 1e-3)
+    e2e_value = scale * e2e_steps / (e2e_ms * 1e-3)
+    total_bytes, prop_bytes = walk_bytes(trace, nnz_p, n, s)
+    peak, peak_src = measured_hbm_peak()
+    # rows are sharded: this rank's propagate launch moves ~1/world of the iterate plus all of W
+    prop_bytes_launch = (prop_bytes / max(steps_per_walk, 1))
+    if world > 1:
+        w_bytes = nnz_p * (s + 4) + 4 * (n + 1)
+        prop_bytes_launch = w_bytes + (prop_bytes_launch - w_bytes) / world
+    achieved = prop_bytes_launch / (prop_ms_per_launch * 1e-3) / 1e9 if prop_ms_per_launch > 0 else 0.0
+    step_ms = walk_ms / max(walk_steps, 1)
+    step_gbs = (total_bytes / max(steps_per_walk, 1)) / (step_ms * 1e-3) / 1e9
+    h2d = M.indptr.size * 8 + M.indices.size * 4 + M.data.size * 8 + n * 4
+
+    line = {
+        "metric": "crwr_walk_steps_per_s", "value": value,
+        "unit": "walk-steps/s" if world == 1 else "walk-steps/s x (markers/8000) [weak scaling aggregate]",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": walk_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": config_dict(wl, world, args.dtype),
+        "walk_steps_per_imputation": steps_per_walk, "us_per_walk_step": 1e3 * step_ms,
+        "imputation_wall_ms_e2e": e2e_ms / args.steps,
+        "roofline": {"bound": "hbm", "kernel": "propagate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": prop_bytes_launch, "us_per_launch": 1e3 * prop_ms_per_launch,
+                     "whole_step": {"bytes": total_bytes / max(steps_per_walk, 1), "us": 1e3 * step_ms,
+                                    "achieved": step_gbs, "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0}},
+        "e2e": {"value": e2e_value, "unit": "walk-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import crwr_oracle as oracle
+        perm = oracle.marker_permutation(n, idx)
+        P = oracle.transition_matrix(M, perm, np.float32)
+        tr = oracle.WalkTrace()
+        t0 = time.perf_counter()
+        oracle.crwr_walk(P, 0.5, 80, 0.01, m, trace=tr)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": len(tr.steps) / dt, "unit": "walk-steps/s", "cores": 1, "kind": "port",
+                                "sample": "one full float32 walk (%d steps, %.2f s) of the same workload; scipy.sparse and "
+                                          "np.percentile are serial: 1 of %d host cores used" % (len(tr.steps), dt, os.cpu_count())}
+    walker.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

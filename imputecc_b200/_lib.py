@@ -54,6 +54,8 @@ _SIGNATURES = {
     "crwr_transition_nnz": (C.c_int64, [_P]),
     "crwr_walk_init": (C.c_int32, [_P, C.c_double, C.c_double, C.c_double, C.c_int32, _P]),
     "crwr_set_variant": (C.c_int32, [_P, C.c_int32]),
+    "crwr_profile": (C.c_int32, [_P, C.c_int32]),
+    "crwr_profile_read": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _P]),
     "crwr_walk_enqueue": (C.c_int32, [_P, C.c_int32, _P]),
     "crwr_step_propagate": (C.c_int32, [_P, _P]),
     "crwr_step_hist": (C.c_int32, [_P, C.c_int32, _P]),

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 #include <cmath>
 
 #include "common.cuh"
@@ -133,6 +134,8 @@ struct crwr_handle_s {
     int variant;                    // hash-table variant of the main propagate kernel
     int grid[2][kNumVariants];      // persistent grid size per dtype/variant
     double rp, perc;
+    bool profile = false;                       // CUDA events around every main propagate launch
+    std::vector<cudaEvent_t> ev;                // start/end pairs
     template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
 };
 
@@ -195,6 +198,11 @@ int launch_propagate(crwr_handle_s* h, int parity, cudaStream_t st) {
     PropArgs<T> a = prop_args<T>(h, parity);
     const int rows = a.n_rows;
     const int* g = h->grid[sizeof(T) == 8 ? 1 : 0];
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profile) {
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
+        cudaEventRecord(e0, st);
+    }
 #define X(TT, LH, KM, W, IDX)                                                                 \
     if (h->variant == IDX) {                                                                  \
         int grid = (rows + W - 1) / W;                                                        \
@@ -206,6 +214,11 @@ int launch_propagate(crwr_handle_s* h, int parity, cudaStream_t st) {
     CRWR_VARIANTS(X, T)
 #undef X
     ++g_launches;
+    if (h->profile) {
+        cudaEventRecord(e1, st);
+        h->ev.push_back(e0);
+        h->ev.push_back(e1);
+    }
     if (cudaGetLastError() != cudaSuccess) return -1;
     const Layout& L = h->L;
     DenseScratch<T> sc;
@@ -401,6 +414,7 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
 }
 
 int32_t crwr_destroy(crwr_handle h) {
+    if (h) for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
     return CRWR_OK;
 }
@@ -526,6 +540,29 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     h->steps_enqueued = 0;
     h->walking = true;
     h->variant = 0;
+    return CRWR_OK;
+}
+
+int32_t crwr_profile(crwr_handle h, int32_t enable) {
+    if (!h) CRWR_FAIL(CRWR_ERR_INVALID, "null handle");
+    h->profile = enable != 0;
+    return CRWR_OK;
+}
+
+int32_t crwr_profile_read(crwr_handle h, double* h_total_ms, int64_t* h_launches, void* stream) {
+    if (!h || !h_total_ms || !h_launches) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    double total = 0.0;
+    long long n = 0;
+    for (size_t i = 0; i + 1 < h->ev.size(); i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) { total += ms; ++n; }
+        cudaEventDestroy(h->ev[i]);
+        cudaEventDestroy(h->ev[i + 1]);
+    }
+    h->ev.clear();
+    *h_total_ms = total;
+    *h_launches = n;
     return CRWR_OK;
 }
 

@@ -165,6 +165,12 @@ int32_t crwr_symmetrise_write(int32_t dtype, int64_t m, const int64_t* d_indptr,
                               const void* d_data, int64_t nnz, void* d_scratch, int64_t scratch_bytes,
                               int64_t* d_out_indptr, int32_t* d_out_indices, void* d_out_data, void* stream);
 
+/* Measurement aid: with profiling enabled every launch of the propagation kernel (the dominant
+ * kernel) is bracketed by CUDA events on the launching stream; read returns the summed duration of
+ * the launches since the last read (launches skipped after the stop rule count as ~0) and clears. */
+int32_t crwr_profile(crwr_handle h, int32_t enable);
+int32_t crwr_profile_read(crwr_handle h, double* h_total_ms, int64_t* h_launches, void* stream);
+
 /* Launch counter: kernels this library launched since the last reset (bench gpu_launches). */
 int64_t crwr_launch_count(int32_t reset);
 

@@ -173,7 +173,8 @@ def test_c2_sized_walk_against_live_oracle(cuda_device, dtype):
     assert [t["nnz_new"] for t in info.trace] == [t.nnz_new for t in tr.steps]
     _assert_close(E, want, "c2ish")
     Es = sp.csr_matrix(E)
-    assert (abs(Es - Es.T) > 0).nnz == 0                                        # E is exactly symmetric
+    asym = abs(Es - Es.T)                       # (b_i e) b_j vs (b_j e) b_i: symmetric up to rounding, as in the reference
+    assert (Es != Es.T).nnz == 0 or asym.max() <= 4 * np.finfo(dtype).eps * Es.max()
 
 
 def test_result_is_independent_of_kernel_size_class_and_large_row_path(cuda_device):
