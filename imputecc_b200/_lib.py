@@ -53,7 +53,7 @@ _SIGNATURES = {
     "crwr_get_transition": (C.c_int32, [_P, _P, _P, _P, _P]),
     "crwr_transition_nnz": (C.c_int64, [_P]),
     "crwr_walk_init": (C.c_int32, [_P, C.c_double, C.c_double, C.c_double, C.c_int32, _P]),
-    "crwr_set_variant": (C.c_int32, [_P, C.c_int32]),
+    "crwr_set_row_hints": (C.c_int32, [_P, C.c_int64, C.c_int64]),
     "crwr_profile": (C.c_int32, [_P, C.c_int32]),
     "crwr_profile_read": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _P]),
     "crwr_walk_enqueue": (C.c_int32, [_P, C.c_int32, _P]),

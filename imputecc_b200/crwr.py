@@ -29,9 +29,6 @@ from ._lib import CRWR_F32, CRWR_F64, CapacityError, Config, Status, StepRecord
 DEFAULT_TOL = 0.01          # imputation.py:120
 DEFAULT_MAX_STEPS = 500     # utility.py:281
 
-# hash-table size classes of the propagation kernel: (accumulator limit, kept-entry limit)
-_VARIANTS = ((768, 256), (1536, 512), (3072, 1024), (6144, 2048))
-
 
 def _torch():
     import torch
@@ -125,13 +122,20 @@ def default_iterate_cap(n_rows: int, n_contigs: int) -> int:
     return int(min(n_rows * n_contigs, max(1 << 22, 2048 * n_rows)))
 
 
-def pick_variant(max_row_len: int, max_kept: int) -> int:
-    need_h = int(max_row_len * 1.3) + 32
-    need_k = int(max_kept * 1.25) + 8
-    for v, (lim, kmax) in enumerate(_VARIANTS):
-        if lim >= need_h and kmax >= need_k:
-            return v
-    return len(_VARIANTS) - 1
+def next_row_hints(max_row_len: int, max_kept: int, perc: float, issued: int):
+    """(longest output row, longest kept operand row) to expect in the next step.
+
+    Sizing hints for the propagation kernel's per-row accumulator (crwr_set_row_hints).  Step 0
+    reads Q = I; step 1 reads the un-cut step-0 rows and fans out two hops; from step 2 on the
+    operand is the cut iterate, whose kept share is observed one step late.
+    """
+    if issued < 1:
+        return 192, 32
+    if issued < 2:
+        return 8 * max_row_len, max_row_len
+    if issued < 3:
+        return max_row_len, int(max_row_len * min(1.0, 2.0 * (1.0 - perc / 100.0) + 0.05))
+    return max_row_len, max_kept
 
 
 def stack_row_blocks(blocks: Sequence[sp.csr_matrix]) -> sp.csr_matrix:
@@ -175,6 +179,7 @@ class Walker:
         self.ws = None
         self.regrows = 0
         self._walk_args = None
+        self.hint_override = None      # tests pin the kernel sizing through this
         self._create()
 
     # -- plumbing ---------------------------------------------------------------------------
@@ -316,30 +321,26 @@ class Walker:
         self.walk_init(rp, perc, tol, max_steps)
         lib, h = self.lib, self.handle
         issued = 0
-        variant = 0
+        hints = next_row_hints(0, 0, perc, 0)
         while True:
             # early steps change shape quickly: poll after each; later run four at a time
             chunk = 1 if issued < 4 else 4
             chunk = min(chunk, max_steps - issued)
-            _lib.check(lib.crwr_set_variant(h, variant))
+            self.set_row_hints(*hints)
             _lib.check(lib.crwr_walk_enqueue(h, chunk, self._stream()))
             issued += chunk
             st = self.poll()
             if st.stop_reason != 0 or issued >= max_steps:
                 return st
-            variant = self._next_variant(st, variant, perc, issued)
+            hints = self.row_hints(st, perc, issued)
 
-    def _next_variant(self, st: Status, variant: int, perc: float, issued: int) -> int:
-        if issued < 2:
-            return pick_variant(4 * st.max_row_len, st.max_row_len)   # no cut yet; two-hop growth ahead
-        if issued < 3:                                                # first cut: kept share not yet observed
-            guess_kept = int(st.max_row_len * min(1.0, 2.0 * (1.0 - perc / 100.0) + 0.05))
-        else:
-            guess_kept = int(st.max_kept)
-        v = pick_variant(st.max_row_len, guess_kept)
-        if st.fallback_rows > max(4, self.rows // 200):
-            v = max(v, min(variant + 1, len(_VARIANTS) - 1))
-        return v
+    def set_row_hints(self, max_row_len: int, max_kept: int):
+        if self.hint_override is not None:
+            max_row_len, max_kept = self.hint_override
+        _lib.check(self.lib.crwr_set_row_hints(self.handle, int(max_row_len), int(max_kept)))
+
+    def row_hints(self, st: Status, perc: float, issued: int):
+        return next_row_hints(int(st.max_row_len), int(st.max_kept), perc, issued)
 
     def trace(self) -> list:
         st = self.poll()

@@ -41,7 +41,6 @@ static long long g_launches = 0;
 
 namespace {
 
-constexpr int kNumVariants = 4;
 constexpr int kDenseWarpsPerCta = 4;
 
 struct Layout {
@@ -131,8 +130,9 @@ struct crwr_handle_s {
     bool have_p;
     bool walking;
     int steps_enqueued;
-    int variant;                    // hash-table variant of the main propagate kernel
-    int grid[2][kNumVariants];      // persistent grid size per dtype/variant
+    PropShape shape;                // run-time sizing of the main propagate kernel
+    int grid;                       // its persistent grid size
+    int max_smem_optin;
     double rp, perc;
     bool profile = false;                       // CUDA events around every main propagate launch
     std::vector<cudaEvent_t> ev;                // start/end pairs
@@ -141,33 +141,46 @@ struct crwr_handle_s {
 
 namespace {
 
-template <typename T, int LOG_H, int KMAX, int WARPS>
-int prepare_variant(int sm_count, int* grid_out) {
-    const size_t smem = PropSmem<T, LOG_H, KMAX>::per_warp * WARPS;
-    cudaError_t e = cudaFuncSetAttribute(propagate_kernel<T, LOG_H, KMAX, WARPS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+int round_up(long long x, int q) { return (int)(((x + q - 1) / q) * q); }
+
+// Sizes the accumulator table / kept list / staging buffers from the caller's row-length hints.
+template <typename T>
+int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept) {
+    const long long n = h->cfg.n_contigs;
+    long long limit = round_up(max_row_len + max_row_len / 3 + 64, 32);
+    if (limit < 256) limit = 256;
+    if (limit > n + 32) limit = round_up(n + 32, 32);
+    long long kmax = round_up(max_kept + max_kept / 4 + 32, 32);
+    if (kmax < 64) kmax = 64;
+    if (kmax > n) kmax = round_up(n, 32);
+    const double avg_deg = h->p_nnz > 0 ? (double)h->p_nnz / (double)n : 8.0;
+    long long scap = round_up((long long)(32.0 * avg_deg * 1.5) + 64, 64);
+    if (scap < 256) scap = 256;
+    if (scap > 4096) scap = 4096;
+    PropShape sh;
+    for (;;) {
+        long long H = round_up(limit + limit / 3 + 32, 32);
+        if (H > 65535) { H = 65504; limit = (H * 3) / 4; }
+        sh.H = (int)H; sh.limit = (int)limit; sh.kmax = (int)kmax; sh.scap = (int)scap;
+        sh.per_warp = prop_smem_per_warp<T>(sh.H, sh.limit, sh.kmax, sh.scap);
+        if ((long long)sh.per_warp <= (long long)h->max_smem_optin) break;
+        // too big for one SM: shrink (oversized rows are deferred to the large-row kernel)
+        if (kmax > 1024 && kmax * 2 > limit) kmax = round_up(kmax / 2, 32);
+        else limit = round_up(limit * 3 / 4, 32);
+    }
+    int w = (int)(57344 / sh.per_warp);
+    if (w < 1) w = 1;
+    if (w > 8) w = 8;
+    sh.warps = w;
+    const size_t smem = sh.per_warp * (size_t)w;
+    cudaError_t e = cudaFuncSetAttribute(propagate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagate_kernel<T, LOG_H, KMAX, WARPS>, WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagate_kernel<T>, w * 32, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
-    *grid_out = per_sm * sm_count;
-    return 0;
-}
-
-// variant table: {LOG_H, KMAX, WARPS}
-#define CRWR_VARIANTS(X, T) X(T, 10, 256, 4, 0) X(T, 11, 512, 2, 1) X(T, 12, 1024, 1, 2) X(T, 13, 2048, 1, 3)
-
-template <typename T>
-int prepare_all(crwr_handle_s* h) {
-    int* g = h->grid[sizeof(T) == 8 ? 1 : 0];
-#define X(TT, LH, KM, W, IDX)                                                  \
-    {                                                                          \
-        int e = prepare_variant<TT, LH, KM, W>(h->sm_count, &g[IDX]);          \
-        if (e) return e;                                                       \
-    }
-    CRWR_VARIANTS(X, T)
-#undef X
+    h->shape = sh;
+    h->grid = per_sm * h->sm_count;
     return 0;
 }
 
@@ -197,22 +210,18 @@ template <typename T>
 int launch_propagate(crwr_handle_s* h, int parity, cudaStream_t st) {
     PropArgs<T> a = prop_args<T>(h, parity);
     const int rows = a.n_rows;
-    const int* g = h->grid[sizeof(T) == 8 ? 1 : 0];
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
         if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
         cudaEventRecord(e0, st);
     }
-#define X(TT, LH, KM, W, IDX)                                                                 \
-    if (h->variant == IDX) {                                                                  \
-        int grid = (rows + W - 1) / W;                                                        \
-        if (grid > g[IDX]) grid = g[IDX];                                                     \
-        if (grid < 1) grid = 1;                                                               \
-        const size_t smem = PropSmem<TT, LH, KM>::per_warp * W;                               \
-        propagate_kernel<TT, LH, KM, W><<<grid, W * 32, smem, st>>>(a);                       \
+    {
+        const PropShape& sh = h->shape;
+        int grid = (rows + sh.warps - 1) / sh.warps;
+        if (grid > h->grid) grid = h->grid;
+        if (grid < 1) grid = 1;
+        propagate_kernel<T><<<grid, sh.warps * 32, sh.per_warp * (size_t)sh.warps, st>>>(a, sh);
     }
-    CRWR_VARIANTS(X, T)
-#undef X
     ++g_launches;
     if (h->profile) {
         cudaEventRecord(e1, st);
@@ -403,8 +412,8 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     h->have_p = false;
     h->walking = false;
     h->steps_enqueued = 0;
-    h->variant = 0;
-    int e = cfg->dtype == CRWR_F64 ? prepare_all<double>(h) : prepare_all<float>(h);
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    int e = cfg->dtype == CRWR_F64 ? configure_shape<double>(h, 192, 32) : configure_shape<float>(h, 192, 32);
     if (e) {
         delete h;
         CRWR_FAIL(CRWR_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
@@ -539,7 +548,6 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     h->perc = perc;
     h->steps_enqueued = 0;
     h->walking = true;
-    h->variant = 0;
     return CRWR_OK;
 }
 
@@ -566,9 +574,12 @@ int32_t crwr_profile_read(crwr_handle h, double* h_total_ms, int64_t* h_launches
     return CRWR_OK;
 }
 
-int32_t crwr_set_variant(crwr_handle h, int32_t variant) {
-    if (!h || variant < 0 || variant >= kNumVariants) CRWR_FAIL(CRWR_ERR_INVALID, "variant out of range");
-    h->variant = variant;
+int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept) {
+    if (!h || max_row_len < 0 || max_kept < 0) CRWR_FAIL(CRWR_ERR_INVALID, "bad row hints");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    int e = h->cfg.dtype == CRWR_F64 ? configure_shape<double>(h, max_row_len, max_kept)
+                                     : configure_shape<float>(h, max_row_len, max_kept);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "kernel sizing failed: %s", cudaGetErrorString((cudaError_t)e));
     return CRWR_OK;
 }
 

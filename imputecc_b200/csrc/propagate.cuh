@@ -89,31 +89,75 @@ __device__ __forceinline__ void write_row(const PropArgs<T>& a, int row, int n_c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Main kernel: shared-memory hash accumulator.  LOG_H: log2 of table slots; KMAX: kept entries
-// of the input row that fit; rows exceeding either bound go to the large-row kernel.
+// Main kernel: shared-memory hash accumulator, sized at run time.
+//
+// Per-warp shared memory (PropShape): accumulator table of H slots (keys + values), first-touch
+// list, the kept operand entries with the extent of their P rows, and a double-buffered staging
+// area into which the P rows of the next batch of up to 32 operand entries are copied with
+// cp.async while the current batch is being accumulated - the dependent chain of a row then runs
+// at shared-memory latency, not at L2/HBM latency.  Rows exceeding the table or the kept list
+// are deferred to the large-row kernel.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int LOG_H, int KMAX>
-struct PropSmem {
-    static constexpr int H = 1 << LOG_H;
-    static constexpr int LIMIT = (H * 3) / 4;
-    static constexpr size_t per_warp = (size_t)H * (sizeof(int32_t) + sizeof(T) + sizeof(uint16_t)) +
-                                       (size_t)KMAX * (sizeof(int32_t) + sizeof(T));
+struct PropShape {
+    int H;        // accumulator slots
+    int limit;    // max distinct output columns held (<= 3/4 H)
+    int kmax;     // max kept operand entries
+    int scap;     // staging capacity (products) per buffer
+    int warps;    // warps per CTA
+    size_t per_warp;
 };
 
-template <typename T, int LOG_H, int KMAX, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) propagate_kernel(PropArgs<T> a) {
-    typedef PropSmem<T, LOG_H, KMAX> S;
-    constexpr int H = S::H;
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+template <typename T>
+__host__ __device__ inline size_t prop_smem_per_warp(int H, int limit, int kmax, int scap) {
+    return align16((size_t)H * sizeof(T)) + align16((size_t)kmax * sizeof(T)) + align16((size_t)2 * scap * sizeof(T)) +
+           align16((size_t)H * 4) + 3 * align16((size_t)kmax * 4) + align16((size_t)2 * scap * 4) +
+           align16((size_t)(limit + 32) * 2);
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_val(float* d, const float* g) { cp_async4(d, g); }
+__device__ __forceinline__ void cp_async_val(double* d, const double* g) { cp_async8(d, g); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ uint32_t hash_slot(int32_t j, int H) {
+    return __umulhi((uint32_t)j * 0x9E3779B1u, (uint32_t)H);
+}
+
+// One batch of operand entries whose P rows are staged together.
+struct Batch {
+    int nb;      // operand entries in the batch (0: none)
+    int len;     // this lane's entry: length of its P row   (lane t <-> entry first+t)
+    int off;     // this lane's entry: offset of its products inside the staging buffer
+    int direct;  // 1: a single entry whose row exceeds the staging buffer; streamed from global
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape sh) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (a.st->done) return;
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    unsigned char* mine = smem_raw + (size_t)warp * S::per_warp;
-    T* tval = reinterpret_cast<T*>(mine);
-    T* kval = tval + H;
-    int32_t* tkey = reinterpret_cast<int32_t*>(kval + KMAX);
-    int32_t* kcol = tkey + H;
-    uint16_t* ord = reinterpret_cast<uint16_t*>(kcol + KMAX);
+    const int H = sh.H, KMAX = sh.kmax, SCAP = sh.scap, LIMIT = sh.limit;
+    unsigned char* p = smem_raw + (size_t)warp * sh.per_warp;
+    T* tval = reinterpret_cast<T*>(p);            p += align16((size_t)H * sizeof(T));
+    T* kval = reinterpret_cast<T*>(p);            p += align16((size_t)KMAX * sizeof(T));
+    T* sval = reinterpret_cast<T*>(p);            p += align16((size_t)2 * SCAP * sizeof(T));
+    int32_t* tkey = reinterpret_cast<int32_t*>(p); p += align16((size_t)H * 4);
+    int32_t* kcol = reinterpret_cast<int32_t*>(p); p += align16((size_t)KMAX * 4);
+    int32_t* kps = reinterpret_cast<int32_t*>(p);  p += align16((size_t)KMAX * 4);
+    int32_t* klen = reinterpret_cast<int32_t*>(p); p += align16((size_t)KMAX * 4);
+    int32_t* scol = reinterpret_cast<int32_t*>(p); p += align16((size_t)2 * SCAP * 4);
+    uint16_t* ord = reinterpret_cast<uint16_t*>(p);
 
     for (int i = lane; i < H; i += 32) tkey[i] = -1;
     __syncwarp();
@@ -121,6 +165,43 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_kernel(PropArgs<T> a) {
     const bool cut_on = a.st->cut_on != 0;
     const T cut = (T)a.st->cut;
     unsigned long long kept_total = 0;
+
+    // Picks the batch starting at operand entry `first` and issues the cp.async copies of its P
+    // rows into staging buffer `buf`.  Uniform across the warp.
+    auto stage = [&](int first, int nk, int buf) -> Batch {
+        Batch bt;
+        bt.nb = 0; bt.len = 0; bt.off = 0; bt.direct = 0;
+        if (first >= nk) return bt;
+        const int idx = first + lane;
+        const int len = idx < nk ? klen[idx] : 0;
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const unsigned fit = __ballot_sync(kFull, idx < nk && incl <= SCAP);
+        // entries are taken in order: the batch is the longest prefix that fits
+        int nb = __ffs(~fit) - 1;                 // number of leading set bits
+        if (fit == kFull) nb = 32;
+        bt.len = len;
+        bt.off = incl - len;
+        if (nb == 0) { bt.nb = 1; bt.direct = 1; return bt; }
+        bt.nb = nb;
+        const int ps = idx < nk ? kps[idx] : 0;
+        int32_t* dc = scol + buf * SCAP;
+        T* dv = sval + buf * SCAP;
+        for (int t = 0; t < nb; ++t) {
+            const int s_ = __shfl_sync(kFull, ps, t);
+            const int l_ = __shfl_sync(kFull, len, t);
+            const int o_ = __shfl_sync(kFull, bt.off, t);
+            for (int e = lane; e < l_; e += 32) {
+                cp_async4(dc + o_ + e, a.p_cols + s_ + e);
+                cp_async_val(dv + o_ + e, a.p_vals + s_ + e);
+            }
+        }
+        return bt;
+    };
 
     for (;;) {
         int row = 0;
@@ -132,65 +213,92 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_kernel(PropArgs<T> a) {
         const long long ptr = a.in.row_ptr[row];
         const int len = a.in.row_len[row];
         int nk = 0;
-        for (int b = 0; b < len; b += 32) {
-            int e = b + lane;
-            int32_t c = 0;
-            T v = (T)0;
-            if (e < len) { c = a.in.cols[ptr + e]; v = a.in.vals[ptr + e]; }
-            bool keep = (e < len) && (!cut_on || v > cut);
-            unsigned m = __ballot_sync(kFull, keep);
-            int pos = nk + __popc(m & lanemask_lt());
-            if (keep && pos < KMAX) { kcol[pos] = c; kval[pos] = v; }
-            nk += __popc(m);
+        for (int b = 0; b < len; b += 128) {
+            int32_t c[4];
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = b + u * 32 + lane;
+                c[u] = 0; v[u] = (T)0;
+                if (e < len) { c[u] = a.in.cols[ptr + e]; v[u] = a.in.vals[ptr + e]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = b + u * 32 + lane;
+                const bool keep = (e < len) && (!cut_on || v[u] > cut);
+                const unsigned m = __ballot_sync(kFull, keep);
+                const int pos = nk + __popc(m & lanemask_lt());
+                if (keep && pos < KMAX) { kcol[pos] = c[u]; kval[pos] = v[u]; }
+                nk += __popc(m);
+            }
         }
         __syncwarp();
-        bool defer = nk > KMAX;
         if (lane == 0) atomicMax(&a.st->max_kept, nk);
+        bool defer = nk > KMAX;
         int count = 0;
         if (!defer) {
             if (cut_on) warp_sort_pairs(kcol, kval, nk);
-            // ---- accumulate products in order of k
-            for (int b = 0; b < nk && !defer; b += 32) {
-                int idx = b + lane;
-                T myq = (T)0;
-                int ps = 0, pe = 0;
-                if (idx < nk) {
-                    int k = kcol[idx];
-                    myq = kval[idx];
-                    ps = __ldg(a.p_indptr + k);
-                    pe = __ldg(a.p_indptr + k + 1);
-                }
-                const int nb = min(32, nk - b);
-                for (int t = 0; t < nb && !defer; ++t) {
+            for (int idx = lane; idx < nk; idx += 32) {
+                const int k = kcol[idx];
+                const int ps = __ldg(a.p_indptr + k);
+                kps[idx] = ps;
+                klen[idx] = __ldg(a.p_indptr + k + 1) - ps;
+            }
+            __syncwarp();
+
+            // ---- accumulate products in order of k, P rows arriving through the staging buffers
+            int first = 0, buf = 0;
+            Batch cur = stage(first, nk, buf);
+            cp_async_commit();
+            while (cur.nb > 0 && !defer) {
+                const int next_first = first + cur.nb;
+                Batch nxt = stage(next_first, nk, buf ^ 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+                __syncwarp();
+                const T myq = (first + lane < nk) ? kval[first + lane] : (T)0;
+                const int32_t* bc = scol + buf * SCAP;
+                const T* bv = sval + buf * SCAP;
+                for (int t = 0; t < cur.nb && !defer; ++t) {
                     const T q = __shfl_sync(kFull, myq, t);
-                    const int s = __shfl_sync(kFull, ps, t);
-                    const int e_end = __shfl_sync(kFull, pe, t);
-                    for (int e0 = s; e0 < e_end; e0 += 32) {
-                        if (count + 32 > S::LIMIT) { defer = true; break; }
+                    const int l_ = __shfl_sync(kFull, cur.len, t);
+                    const int o_ = __shfl_sync(kFull, cur.off, t);
+                    const int gs = cur.direct ? kps[first] : 0;
+                    for (int e0 = 0; e0 < l_; e0 += 32) {
+                        if (count + 32 > LIMIT) { defer = true; break; }
                         const int e = e0 + lane;
                         bool is_new = false;
                         uint32_t slot = 0;
-                        if (e < e_end) {
-                            const int32_t j = __ldg(a.p_cols + e);
-                            const T prod = mul_rn(q, __ldg(a.p_vals + e));
-                            slot = hash_col(j, LOG_H);
+                        if (e < l_) {
+                            int32_t j;
+                            T pv;
+                            if (cur.direct) { j = __ldg(a.p_cols + gs + e); pv = __ldg(a.p_vals + gs + e); }
+                            else { j = bc[o_ + e]; pv = bv[o_ + e]; }
+                            const T prod = mul_rn(q, pv);
+                            slot = hash_slot(j, H);
                             for (;;) {
-                                int32_t kk = tkey[slot];
-                                if (kk == j) { tval[slot] = add_rn(tval[slot], prod); break; }
+                                const int32_t kk = tkey[slot];
+                                const T curv = tval[slot];
+                                if (kk == j) { tval[slot] = add_rn(curv, prod); break; }
                                 if (kk == -1) {
-                                    int32_t old = atomicCAS(&tkey[slot], -1, j);
+                                    const int32_t old = atomicCAS(&tkey[slot], -1, j);
                                     if (old == -1) { tval[slot] = prod; is_new = true; break; }
                                 }
-                                slot = (slot + 1) & (H - 1);
+                                slot = slot + 1 == (uint32_t)H ? 0u : slot + 1;
                             }
                         }
-                        unsigned nm = __ballot_sync(kFull, is_new);
+                        const unsigned nm = __ballot_sync(kFull, is_new);
                         if (is_new) ord[count + __popc(nm & lanemask_lt())] = (uint16_t)slot;
                         count += __popc(nm);
                         __syncwarp();
                     }
                 }
+                first = next_first;
+                buf ^= 1;
+                cur = nxt;
             }
+            cp_async_wait<0>();
+            __syncwarp();
         }
         if (defer) {
             // undo and hand the row to the large-row kernel
@@ -205,22 +313,22 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_kernel(PropArgs<T> a) {
         const int32_t dcol = a.row_begin + row;
         int dslot = -1;
         {
-            uint32_t slot = hash_col(dcol, LOG_H);
+            uint32_t slot = hash_slot(dcol, H);
             for (;;) {
-                int32_t kk = tkey[slot];
+                const int32_t kk = tkey[slot];
                 if (kk == dcol) { dslot = (int)slot; break; }
                 if (kk == -1) break;
-                slot = (slot + 1) & (H - 1);
+                slot = slot + 1 == (uint32_t)H ? 0u : slot + 1;
             }
         }
         const bool diag_new = dslot < 0;
         double s1 = 0.0;
         int nz = 0;
         for (int b = 0; b < count; b += 32) {
-            int i = b + lane;
+            const int i = b + lane;
             bool one = false;
             if (i < count) {
-                int slot = ord[i];
+                const int slot = ord[i];
                 T v = mul_rn(a.scale, tval[slot]);
                 if (slot == dslot) v = add_rn(v, a.restart);
                 tval[slot] = v;
@@ -238,13 +346,13 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_kernel(PropArgs<T> a) {
         for (int idx = lane; idx < nk; idx += 32) {
             const int32_t j = kcol[idx];
             const T oldv = kval[idx];
-            uint32_t slot = hash_col(j, LOG_H);
+            uint32_t slot = hash_slot(j, H);
             bool found = false;
             for (;;) {
-                int32_t kk = tkey[slot];
+                const int32_t kk = tkey[slot];
                 if (kk == j) { found = true; break; }
                 if (kk == -1) break;
-                slot = (slot + 1) & (H - 1);
+                slot = slot + 1 == (uint32_t)H ? 0u : slot + 1;
             }
             T newv = (T)0;
             if (found) newv = tval[slot];
@@ -259,7 +367,7 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_kernel(PropArgs<T> a) {
         const int shift = diag_new ? 1 : 0;
         write_row(a, row, n_cand, nz, [&](int i, int32_t& c, T& v) {
             if (i < shift) { c = dcol; v = a.restart; }
-            else { int slot = ord[i - shift]; c = tkey[slot]; v = tval[slot]; }
+            else { const int slot = ord[i - shift]; c = tkey[slot]; v = tval[slot]; }
         });
         __syncwarp();
         for (int i = lane; i < count; i += 32) tkey[ord[i]] = -1;

@@ -56,14 +56,14 @@ class CudaPhases:
         ptr = C.c_void_p(gathered.data_ptr()) if gathered is not None else C.c_void_p(0)
         _lib.check(self.w.lib.crwr_step_finish(self.w.handle, ptr, self.w._stream()))
 
-    def set_variant(self, v):
-        _lib.check(self.w.lib.crwr_set_variant(self.w.handle, v))
+    def set_row_hints(self, hints):
+        self.w.set_row_hints(*hints)
 
     def poll(self):
         return self.w.poll()
 
-    def next_variant(self, st, variant, perc, issued):
-        return self.w._next_variant(st, variant, perc, issued)
+    def row_hints(self, st, perc, issued):
+        return self.w.row_hints(st, perc, issued)
 
 
 def _all_gather_blocks(dist, block, world, group):
@@ -90,23 +90,24 @@ class TorchComm:
     def all_gather(self, block):
         return _all_gather_blocks(self.dist, block, self.world, self.group)
 
-    def max_int(self, value: int, like) -> int:
+    def max_ints(self, values, like):
         torch = _torch()
-        v = torch.tensor([value], dtype=torch.int64, device=like.device)
+        v = torch.tensor(list(values), dtype=torch.int64, device=like.device)
         self.dist.all_reduce(v, op=self.dist.ReduceOp.MAX, group=self.group)
-        return int(v.item())
+        return tuple(int(x) for x in v.cpu())
 
 
 def run_sharded_walk(phases, comm, perc, max_steps):
     """Drive utility.py:281-304 across the shards behind ``comm``; every rank issues the same sequence.
 
     ``phases`` is a CudaPhases (the CPU tests pass an object with the same methods)."""
+    from .crwr import next_row_hints
     issued = 0
-    variant = 0
+    hints = next_row_hints(0, 0, perc, 0)
     while True:
         chunk = 1 if issued < 4 else 4
         chunk = min(chunk, max_steps - issued)
-        phases.set_variant(variant)
+        phases.set_row_hints(hints)
         for _ in range(chunk):
             phases.propagate()
             if issued >= 1:
@@ -125,8 +126,8 @@ def run_sharded_walk(phases, comm, perc, max_steps):
         st = phases.poll()
         if st.stop_reason != 0 or issued >= max_steps:
             return st
-        # the size class affects speed only, never results; keep the shards in lockstep anyway
-        variant = comm.max_int(phases.next_variant(st, variant, perc, issued), phases.exchange(0))
+        # sizing hints affect speed only, never results; use the largest over the shards
+        hints = comm.max_ints(phases.row_hints(st, perc, issued), phases.exchange(0))
 
 
 def gather_row_blocks(dist, group, ip, ix, dt, rows_of_rank, m):

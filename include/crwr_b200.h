@@ -115,10 +115,11 @@ int32_t crwr_get_transition(crwr_handle h, int32_t* d_indptr, int32_t* d_indices
  * the reference (imputation.py:120, utility.py:281). */
 int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_t max_steps, void* stream);
 
-/* Hash-table size class of the propagation kernel (0..3: 1024/2048/4096/8192 accumulator slots per
- * restart row); rows that do not fit take the large-row path.  Host policy picks it from
- * crwr_status.max_row_len / fallback_rows. */
-int32_t crwr_set_variant(crwr_handle h, int32_t variant);
+/* Sizing hints for the propagation kernel: the longest output row and the longest kept operand
+ * row to expect.  They size the per-row shared-memory accumulator; rows that do not fit take the
+ * large-row path, so hints affect speed only, never results.  Host policy derives them from
+ * crwr_status.max_row_len / max_kept. */
+int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept);
 int64_t crwr_transition_nnz(crwr_handle h);
 
 /* Enqueue up to n_steps walk steps (utility.py:282-304).  Stop rules are evaluated on the

@@ -38,11 +38,11 @@ class NumpyPhases:
     def exchange(self, which):
         return self.x[which]
 
-    def set_variant(self, v):
+    def set_row_hints(self, hints):
         pass
 
-    def next_variant(self, st, variant, perc, issued):
-        return 0
+    def row_hints(self, st, perc, issued):
+        return (0, 0)
 
     def propagate(self):
         if self.done:

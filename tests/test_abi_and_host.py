@@ -122,16 +122,13 @@ def test_shard_rows_partitions():
         crwr.shard_rows(3, 4)
 
 
-def test_pick_variant_monotone():
-    assert crwr.pick_variant(100, 20) == 0
-    assert crwr.pick_variant(1100, 250) == 1
-    assert crwr.pick_variant(1100, 600) == 2
-    assert crwr.pick_variant(100000, 50000) == 3
-    last = 0
-    for L in range(0, 8000, 50):
-        v = crwr.pick_variant(L, L // 5)
-        assert v >= last
-        last = v
+def test_next_row_hints_policy():
+    assert crwr.next_row_hints(0, 0, 80, 0) == (192, 32)
+    out, kept = crwr.next_row_hints(30, 1, 80, 1)            # un-cut step-0 rows feed step 1
+    assert kept == 30 and out >= 4 * 30
+    out, kept = crwr.next_row_hints(1000, 30, 80, 2)         # first cut: kept share guessed from perc
+    assert out == 1000 and 400 <= kept <= 500
+    assert crwr.next_row_hints(1000, 180, 80, 7) == (1000, 180)
 
 
 def test_stack_row_blocks():

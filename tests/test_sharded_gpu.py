@@ -22,7 +22,7 @@ class MultiPhases:
         return [p.exchange(which) for p in self.p]
 
     def __getattr__(self, name):
-        if name in ("propagate", "hist", "scan", "gather", "set_variant"):
+        if name in ("propagate", "hist", "scan", "gather", "set_row_hints"):
             return lambda *a: [getattr(p, name)(*a) for p in self.p]
         raise AttributeError(name)
 
@@ -35,8 +35,9 @@ class MultiPhases:
         assert len({(s.steps_done, s.stop_reason) for s in sts}) == 1      # identical decisions on every shard
         return sts[0]
 
-    def next_variant(self, st, variant, perc, issued):
-        return max(p.next_variant(p.poll(), variant, perc, issued) for p in self.p)
+    def row_hints(self, st, perc, issued):
+        hs = [p.row_hints(p.poll(), perc, issued) for p in self.p]
+        return max(h[0] for h in hs), max(h[1] for h in hs)
 
 
 class LoopbackComm:
@@ -48,8 +49,8 @@ class LoopbackComm:
     def all_gather(self, blocks):
         return torch.cat(blocks)
 
-    def max_int(self, value, like):
-        return value
+    def max_ints(self, values, like):
+        return tuple(values)
 
 
 @pytest.mark.parametrize("shards", [2, 3])
