@@ -242,6 +242,8 @@ def main():
     launches = int(lib.crwr_launch_count(0))
     walk_ms = sum(a.elapsed_time(b) for a, b in ev)
     trace = walker.trace()
+    if rank == 0:
+        print("trace:", [(t["nnz_in"], t["nnz_new"], t["max_row_len"], t["max_kept"], t["fallback_rows"]) for t in trace], file=sys.stderr)
 
     # ---- dominant kernel, live (CUDA events inside the library around each propagate launch) ----
     lib.crwr_profile(walker.handle, 1)

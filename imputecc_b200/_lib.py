@@ -20,7 +20,8 @@ class Config(C.Structure):
 
 class StepRecord(C.Structure):
     _fields_ = [("nnz_in", C.c_int64), ("nnz_new", C.c_int64), ("cut", C.c_double), ("delta", C.c_double),
-                ("cut_applied", C.c_int32), ("plateau_hits", C.c_int32)]
+                ("cut_applied", C.c_int32), ("plateau_hits", C.c_int32), ("fallback_rows", C.c_int32),
+                ("max_row_len", C.c_int32), ("max_kept", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Status(C.Structure):
@@ -54,6 +55,7 @@ _SIGNATURES = {
     "crwr_transition_nnz": (C.c_int64, [_P]),
     "crwr_walk_init": (C.c_int32, [_P, C.c_double, C.c_double, C.c_double, C.c_int32, _P]),
     "crwr_set_row_hints": (C.c_int32, [_P, C.c_int64, C.c_int64]),
+    "crwr_get_shape": (C.c_int32, [_P, C.POINTER(C.c_int64)]),
     "crwr_profile": (C.c_int32, [_P, C.c_int32]),
     "crwr_profile_read": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _P]),
     "crwr_walk_enqueue": (C.c_int32, [_P, C.c_int32, _P]),

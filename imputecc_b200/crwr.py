@@ -351,7 +351,8 @@ class Walker:
         for i in range(n):
             r = buf[i]
             out.append(dict(step=i, nnz_in=int(r.nnz_in), nnz_new=int(r.nnz_new), cut=float(r.cut),
-                            cut_applied=bool(r.cut_applied), delta=float(r.delta), plateau_hits=int(r.plateau_hits)))
+                            cut_applied=bool(r.cut_applied), delta=float(r.delta), plateau_hits=int(r.plateau_hits),
+                            fallback_rows=int(r.fallback_rows), max_row_len=int(r.max_row_len), max_kept=int(r.max_kept)))
         for a, b in zip(out, out[1:]):
             a["nnz_kept"] = b["nnz_in"] if a["cut_applied"] else a["nnz_new"]
         return out

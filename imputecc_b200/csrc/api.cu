@@ -154,7 +154,7 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
     if (kmax < 64) kmax = 64;
     if (kmax > n) kmax = round_up(n, 32);
     const double avg_deg = h->p_nnz > 0 ? (double)h->p_nnz / (double)n : 8.0;
-    long long scap = round_up((long long)(32.0 * avg_deg * 1.5) + 64, 64);
+    long long scap = round_up((long long)(32.0 * avg_deg * 1.15) + 32, 64);
     if (scap < 256) scap = 256;
     if (scap > 4096) scap = 4096;
     PropShape sh;
@@ -583,6 +583,13 @@ int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept)
     return CRWR_OK;
 }
 
+int32_t crwr_get_shape(crwr_handle h, int64_t* h_out8) {
+    if (!h || !h_out8) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    h_out8[0] = h->shape.H; h_out8[1] = h->shape.limit; h_out8[2] = h->shape.kmax; h_out8[3] = h->shape.scap;
+    h_out8[4] = h->shape.warps; h_out8[5] = (int64_t)h->shape.per_warp; h_out8[6] = h->grid; h_out8[7] = h->sm_count;
+    return CRWR_OK;
+}
+
 int32_t crwr_walk_enqueue(crwr_handle h, int32_t n_steps, void* stream) {
     if (!h || !h->walking) CRWR_FAIL(CRWR_ERR_STATE, "crwr_walk_init first");
     if (h->cfg.n_shards != 1)
@@ -671,7 +678,7 @@ int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
     out->capacity_overflow = s.capacity_overflow | (s.select_overflow << 1);
     out->fallback_rows = s.last_fallback_rows;
     out->nnz_iterate = (int64_t)s.cursor;
-    out->max_row_len = s.max_row_len;
+    out->max_row_len = s.last_max_row_len;
     out->max_kept = s.last_max_kept;
     out->last_cut = s.cut;
     out->last_delta = s.last_delta;

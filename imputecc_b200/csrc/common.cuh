@@ -81,6 +81,8 @@ struct WalkState {
     int32_t max_row_len;
     int32_t max_kept;               // longest kept list read this step
     int32_t last_max_kept;
+    int32_t last_max_row_len;
+    int32_t pad1;
     int32_t capacity_overflow;      // sticky
     int32_t select_overflow;        // sticky: candidate buffer overflow
     // select

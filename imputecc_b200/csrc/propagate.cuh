@@ -111,8 +111,9 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 
 template <typename T>
 __host__ __device__ inline size_t prop_smem_per_warp(int H, int limit, int kmax, int scap) {
-    return align16((size_t)H * sizeof(T)) + align16((size_t)kmax * sizeof(T)) + align16((size_t)2 * scap * sizeof(T)) +
-           align16((size_t)H * 4) + 3 * align16((size_t)kmax * 4) + align16((size_t)2 * scap * 4) +
+    const size_t ht = (size_t)H + 64;
+    return align16(ht * sizeof(T)) + align16((size_t)kmax * sizeof(T)) + 2 * align16((size_t)2 * scap * sizeof(T)) +
+           align16(ht * 4) + 3 * align16((size_t)kmax * 4) + align16((size_t)2 * scap * 4) +
            align16((size_t)(limit + 32) * 2);
 }
 
@@ -133,13 +134,63 @@ __device__ __forceinline__ uint32_t hash_slot(int32_t j, int H) {
     return __umulhi((uint32_t)j * 0x9E3779B1u, (uint32_t)H);
 }
 
-// One batch of operand entries whose P rows are staged together.
-struct Batch {
-    int nb;      // operand entries in the batch (0: none)
-    int len;     // this lane's entry: length of its P row   (lane t <-> entry first+t)
-    int off;     // this lane's entry: offset of its products inside the staging buffer
-    int direct;  // 1: a single entry whose row exceeds the staging buffer; streamed from global
-};
+// Ascending sort of up to 256 (column, value) pairs held in shared memory, by one warp, in
+// registers: 8 keys per lane, bitonic network with shuffles.  Keys are (column << 32 | position);
+// values are gathered afterwards through the positions.
+template <typename T, int R>
+__device__ __forceinline__ void warp_sort_kept_regs(int32_t* kcol, T* kval, T* scratch, int n) {
+    const int lane = lane_id();
+    unsigned long long key[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = r * 32 + lane;          // element i lives in register r of lane (i & 31)
+        key[r] = i < n ? (((unsigned long long)(uint32_t)kcol[i] << 32) | (unsigned)i) : ~0ull;
+    }
+    // index of element = r*32 + lane: bit positions 0..4 = lane bits, 5..7 = register bits
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int rj = j >> 5;        // partner differs in a register bit
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & rj) == 0) {
+                        const int i = r * 32 + lane;
+                        const bool asc = (i & k) == 0;
+                        unsigned long long x = key[r], y = key[r | rj];
+                        const bool sw = (x > y) == asc;
+                        key[r] = sw ? y : x;
+                        key[r | rj] = sw ? x : y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = r * 32 + lane;
+                    const bool asc = (i & k) == 0;
+                    const unsigned long long other = __shfl_xor_sync(kFull, key[r], j);
+                    const bool lower = (lane & j) == 0;
+                    // the lower index keeps the min when ascending
+                    const bool take_min = lower == asc;
+                    key[r] = take_min ? (key[r] < other ? key[r] : other) : (key[r] > other ? key[r] : other);
+                }
+            }
+        }
+    }
+    // gather values through the sorted positions (scratch holds a copy of the unsorted values)
+    for (int i = lane; i < n; i += 32) scratch[i] = kval[i];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = r * 32 + lane;
+        if (i < n) {
+            kcol[i] = (int32_t)(key[r] >> 32);
+            kval[i] = scratch[(unsigned)(key[r] & 0xffffffffu)];
+        }
+    }
+    __syncwarp();
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape sh) {
@@ -148,59 +199,79 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const int H = sh.H, KMAX = sh.kmax, SCAP = sh.scap, LIMIT = sh.limit;
+    // table of H slots plus 64 slots of probe overrun; the last one is a never-claimed sentinel that
+    // stops a probe and sends it back to slot 0 (so the probe loop itself needs no wrap test)
+    const int HT = H + 64;
     unsigned char* p = smem_raw + (size_t)warp * sh.per_warp;
-    T* tval = reinterpret_cast<T*>(p);            p += align16((size_t)H * sizeof(T));
+    T* tval = reinterpret_cast<T*>(p);            p += align16((size_t)HT * sizeof(T));
     T* kval = reinterpret_cast<T*>(p);            p += align16((size_t)KMAX * sizeof(T));
     T* sval = reinterpret_cast<T*>(p);            p += align16((size_t)2 * SCAP * sizeof(T));
-    int32_t* tkey = reinterpret_cast<int32_t*>(p); p += align16((size_t)H * 4);
+    T* sq = reinterpret_cast<T*>(p);              p += align16((size_t)2 * SCAP * sizeof(T));
+    int32_t* tkey = reinterpret_cast<int32_t*>(p); p += align16((size_t)HT * 4);
     int32_t* kcol = reinterpret_cast<int32_t*>(p); p += align16((size_t)KMAX * 4);
     int32_t* kps = reinterpret_cast<int32_t*>(p);  p += align16((size_t)KMAX * 4);
     int32_t* klen = reinterpret_cast<int32_t*>(p); p += align16((size_t)KMAX * 4);
     int32_t* scol = reinterpret_cast<int32_t*>(p); p += align16((size_t)2 * SCAP * 4);
     uint16_t* ord = reinterpret_cast<uint16_t*>(p);
 
-    for (int i = lane; i < H; i += 32) tkey[i] = -1;
+    for (int i = lane; i < HT; i += 32) tkey[i] = -1;
     __syncwarp();
 
     const bool cut_on = a.st->cut_on != 0;
     const T cut = (T)a.st->cut;
     unsigned long long kept_total = 0;
+    const int32_t* __restrict__ pcols = a.p_cols;
+    const T* __restrict__ pvals = a.p_vals;
 
-    // Picks the batch starting at operand entry `first` and issues the cp.async copies of its P
-    // rows into staging buffer `buf`.  Uniform across the warp.
-    auto stage = [&](int first, int nk, int buf) -> Batch {
-        Batch bt;
-        bt.nb = 0; bt.len = 0; bt.off = 0; bt.direct = 0;
-        if (first >= nk) return bt;
+    // Copies the P rows of up to 32 operand entries (lane t <-> entry first+t, each lane streams its
+    // own row with cp.async) into staging buffer `buf`, together with the entry's value q.  Returns
+    // the number of entries taken (the longest prefix whose products fit) and the product count.
+    auto stage = [&](int first, int nk, int buf, int& n_prod) -> int {
+        n_prod = 0;
+        if (first >= nk) return 0;
         const int idx = first + lane;
         const int len = idx < nk ? klen[idx] : 0;
         int incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(kFull, incl, o);
+            const int v = __shfl_up_sync(kFull, incl, o);
             if (lane >= o) incl += v;
         }
         const unsigned fit = __ballot_sync(kFull, idx < nk && incl <= SCAP);
-        // entries are taken in order: the batch is the longest prefix that fits
-        int nb = __ffs(~fit) - 1;                 // number of leading set bits
-        if (fit == kFull) nb = 32;
-        bt.len = len;
-        bt.off = incl - len;
-        if (nb == 0) { bt.nb = 1; bt.direct = 1; return bt; }
-        bt.nb = nb;
-        const int ps = idx < nk ? kps[idx] : 0;
+        int nb = fit == kFull ? 32 : __ffs(~fit) - 1;
         int32_t* dc = scol + buf * SCAP;
         T* dv = sval + buf * SCAP;
-        for (int t = 0; t < nb; ++t) {
-            const int s_ = __shfl_sync(kFull, ps, t);
-            const int l_ = __shfl_sync(kFull, len, t);
-            const int o_ = __shfl_sync(kFull, bt.off, t);
-            for (int e = lane; e < l_; e += 32) {
-                cp_async4(dc + o_ + e, a.p_cols + s_ + e);
-                cp_async_val(dv + o_ + e, a.p_vals + s_ + e);
+        T* dq = sq + buf * SCAP;
+        if (nb == 0) {
+            // a single P row longer than the staging buffer: its first SCAP entries now, the rest by
+            // re-entering with the extent advanced (kps/klen of the entry are updated in place)
+            const int ps0 = kps[first];
+            const T q0 = kval[first];
+            for (int e = lane; e < SCAP; e += 32) {
+                cp_async4(dc + e, pcols + ps0 + e);
+                cp_async_val(dv + e, pvals + ps0 + e);
+                dq[e] = q0;
+            }
+            __syncwarp();
+            if (lane == 0) { kps[first] = ps0 + SCAP; klen[first] -= SCAP; }
+            __syncwarp();
+            n_prod = SCAP;
+            return 0;                      // entry not finished: `first` does not advance
+        }
+        if (lane < nb) {
+            const int off = incl - len;
+            const int ps = kps[idx];
+            const T q = kval[idx];
+            const int32_t* gc = pcols + ps;
+            const T* gv = pvals + ps;
+            for (int e = 0; e < len; ++e) {
+                cp_async4(dc + off + e, gc + e);
+                cp_async_val(dv + off + e, gv + e);
+                dq[off + e] = q;
             }
         }
-        return bt;
+        n_prod = __shfl_sync(kFull, incl, nb - 1);
+        return nb;
     };
 
     for (;;) {
@@ -212,6 +283,8 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
         // ---- read the row, dropping entries at or below the previous cut (strict >, utility.py:290)
         const long long ptr = a.in.row_ptr[row];
         const int len = a.in.row_len[row];
+        const int32_t* __restrict__ rc = a.in.cols + ptr;
+        const T* __restrict__ rv = a.in.vals + ptr;
         int nk = 0;
         for (int b = 0; b < len; b += 128) {
             int32_t c[4];
@@ -220,7 +293,7 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
             for (int u = 0; u < 4; ++u) {
                 const int e = b + u * 32 + lane;
                 c[u] = 0; v[u] = (T)0;
-                if (e < len) { c[u] = a.in.cols[ptr + e]; v[u] = a.in.vals[ptr + e]; }
+                if (e < len) { c[u] = rc[e]; v[u] = rv[e]; }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -237,7 +310,13 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
         bool defer = nk > KMAX;
         int count = 0;
         if (!defer) {
-            if (cut_on) warp_sort_pairs(kcol, kval, nk);
+            if (cut_on && nk > 1) {
+                if (nk <= 32) warp_sort_kept_regs<T, 1>(kcol, kval, sval, nk);
+                else if (nk <= 64) warp_sort_kept_regs<T, 2>(kcol, kval, sval, nk);
+                else if (nk <= 128) warp_sort_kept_regs<T, 4>(kcol, kval, sval, nk);
+                else if (nk <= 256) warp_sort_kept_regs<T, 8>(kcol, kval, sval, nk);
+                else warp_sort_pairs(kcol, kval, nk);
+            }
             for (int idx = lane; idx < nk; idx += 32) {
                 const int k = kcol[idx];
                 const int ps = __ldg(a.p_indptr + k);
@@ -246,56 +325,79 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
             }
             __syncwarp();
 
-            // ---- accumulate products in order of k, P rows arriving through the staging buffers
-            int first = 0, buf = 0;
-            Batch cur = stage(first, nk, buf);
+            // ---- the row's products in scipy's order (k ascending, then P-row order), 32 per round;
+            // batch b+1 is copied into shared memory (cp.async) while batch b is accumulated.
+            int first = 0, buf = 0, n_cur = 0, n_nxt = 0;
+            int nb_cur = stage(first, nk, buf, n_cur);
             cp_async_commit();
-            while (cur.nb > 0 && !defer) {
-                const int next_first = first + cur.nb;
-                Batch nxt = stage(next_first, nk, buf ^ 1);
+            while (n_cur > 0 || nb_cur > 0) {
+                const int next_first = first + nb_cur;
+                const int nb_nxt = stage(next_first, nk, buf ^ 1, n_nxt);
                 cp_async_commit();
                 cp_async_wait<1>();
                 __syncwarp();
-                const T myq = (first + lane < nk) ? kval[first + lane] : (T)0;
                 const int32_t* bc = scol + buf * SCAP;
                 const T* bv = sval + buf * SCAP;
-                for (int t = 0; t < cur.nb && !defer; ++t) {
-                    const T q = __shfl_sync(kFull, myq, t);
-                    const int l_ = __shfl_sync(kFull, cur.len, t);
-                    const int o_ = __shfl_sync(kFull, cur.off, t);
-                    const int gs = cur.direct ? kps[first] : 0;
-                    for (int e0 = 0; e0 < l_; e0 += 32) {
-                        if (count + 32 > LIMIT) { defer = true; break; }
-                        const int e = e0 + lane;
-                        bool is_new = false;
-                        uint32_t slot = 0;
-                        if (e < l_) {
-                            int32_t j;
-                            T pv;
-                            if (cur.direct) { j = __ldg(a.p_cols + gs + e); pv = __ldg(a.p_vals + gs + e); }
-                            else { j = bc[o_ + e]; pv = bv[o_ + e]; }
-                            const T prod = mul_rn(q, pv);
-                            slot = hash_slot(j, H);
-                            for (;;) {
-                                const int32_t kk = tkey[slot];
-                                const T curv = tval[slot];
-                                if (kk == j) { tval[slot] = add_rn(curv, prod); break; }
-                                if (kk == -1) {
-                                    const int32_t old = atomicCAS(&tkey[slot], -1, j);
-                                    if (old == -1) { tval[slot] = prod; is_new = true; break; }
-                                }
-                                slot = slot + 1 == (uint32_t)H ? 0u : slot + 1;
-                            }
+                const T* bq = sq + buf * SCAP;
+                // round r+1's products and their duplicate groups (MATCH) are fetched while round r probes
+                int32_t j_n = -1 - lane;
+                T prod_n = (T)0;
+                if (lane < n_cur) { j_n = bc[lane]; prod_n = mul_rn(bq[lane], bv[lane]); }
+                unsigned peers_n = __match_any_sync(kFull, j_n);
+                for (int r0 = 0; r0 < n_cur; r0 += 32) {
+                    if (count + 32 > LIMIT) { defer = true; break; }
+                    const int32_t j = j_n;
+                    const T prod = prod_n;
+                    const unsigned peers = peers_n;
+                    const bool active = r0 + lane < n_cur;
+                    {
+                        const int fn = r0 + 32 + lane;
+                        j_n = -1 - lane;
+                        prod_n = (T)0;
+                        if (fn < n_cur) { j_n = bc[fn]; prod_n = mul_rn(bq[fn], bv[fn]); }
+                        peers_n = __match_any_sync(kFull, j_n);
+                    }
+                    // lanes holding the same column: the lowest one (earliest product) owns the slot and
+                    // adds the others' products in lane order = scipy's order
+                    const bool leader = active && ((peers & lanemask_lt()) == 0u);
+                    const bool dup = __any_sync(kFull, (peers & (peers - 1u)) != 0u);
+                    bool is_new = false;
+                    uint32_t slot = 0;
+                    T acc = prod;
+                    if (leader) {
+                        slot = hash_slot(j, H);
+                        for (;;) {
+                            int32_t kk = tkey[slot];
+                            while (kk != j && kk != -1) kk = tkey[++slot];     // read-only probe
+                            if (kk == j) { acc = add_rn(tval[slot], prod); break; }
+                            if (slot == (uint32_t)(HT - 1)) { slot = 0; continue; }   // sentinel slot: wrap
+                            if (atomicCAS(&tkey[slot], -1, j) == -1) { is_new = true; break; }
+                            // lost the empty slot to another column of this round: keep probing
                         }
-                        const unsigned nm = __ballot_sync(kFull, is_new);
+                    }
+                    if (dup) {
+                        unsigned rem = peers & (peers - 1u);       // peers after the leader
+                        const int maxmult = __reduce_max_sync(kFull, __popc(peers));
+                        for (int s_ = 1; s_ < maxmult; ++s_) {
+                            const int src = rem ? (__ffs(rem) - 1) : lane;
+                            const T other = __shfl_sync(kFull, prod, src);
+                            if (leader && rem) acc = add_rn(acc, other);
+                            rem &= rem - 1u;
+                        }
+                    }
+                    if (leader) tval[slot] = acc;
+                    const unsigned nm = __ballot_sync(kFull, is_new);
+                    if (nm) {
                         if (is_new) ord[count + __popc(nm & lanemask_lt())] = (uint16_t)slot;
                         count += __popc(nm);
-                        __syncwarp();
                     }
+                    __syncwarp();
                 }
+                if (defer) break;
                 first = next_first;
                 buf ^= 1;
-                cur = nxt;
+                nb_cur = nb_nxt;
+                n_cur = n_nxt;
             }
             cp_async_wait<0>();
             __syncwarp();
@@ -317,8 +419,11 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
             for (;;) {
                 const int32_t kk = tkey[slot];
                 if (kk == dcol) { dslot = (int)slot; break; }
-                if (kk == -1) break;
-                slot = slot + 1 == (uint32_t)H ? 0u : slot + 1;
+                if (kk == -1) {
+                    if (slot == (uint32_t)(HT - 1)) { slot = 0; continue; }
+                    break;
+                }
+                ++slot;
             }
         }
         const bool diag_new = dslot < 0;
@@ -351,8 +456,11 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
             for (;;) {
                 const int32_t kk = tkey[slot];
                 if (kk == j) { found = true; break; }
-                if (kk == -1) break;
-                slot = slot + 1 == (uint32_t)H ? 0u : slot + 1;
+                if (kk == -1) {
+                    if (slot == (uint32_t)(HT - 1)) { slot = 0; continue; }
+                    break;
+                }
+                ++slot;
             }
             T newv = (T)0;
             if (found) newv = tval[slot];

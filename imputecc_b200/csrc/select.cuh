@@ -334,6 +334,10 @@ __global__ void __launch_bounds__(1024) finish_step_kernel(FinishArgs a) {
             rec.delta = delta;
             rec.cut_applied = cut_applied;
             rec.plateau_hits = st->plateau;
+            rec.fallback_rows = (int)fb;
+            rec.max_row_len = st->max_row_len;
+            rec.max_kept = st->max_kept;
+            rec.reserved = 0;
             a.trace[step] = rec;
         }
         st->last_delta = delta;
@@ -347,6 +351,7 @@ __global__ void __launch_bounds__(1024) finish_step_kernel(FinishArgs a) {
         st->stop_reason = reason;
         st->last_fallback_rows = (int)fb;
         st->last_max_kept = st->max_kept;
+        st->last_max_row_len = st->max_row_len;
         st->max_kept = 0;
         if (!done) {
             // counters of the next step (when stopping, cursor/max_row_len keep describing the result)

@@ -72,6 +72,10 @@ typedef struct crwr_step_record {
     double delta;       /* ||Q_prev - Q_new||_F */
     int32_t cut_applied;
     int32_t plateau_hits;
+    int32_t fallback_rows;  /* rows that took the large-row path in this step */
+    int32_t max_row_len;    /* longest row of the step's product */
+    int32_t max_kept;       /* longest kept operand row read by the step */
+    int32_t reserved;
 } crwr_step_record;
 
 typedef struct crwr_status {
@@ -121,6 +125,8 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
  * crwr_status.max_row_len / max_kept. */
 int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept);
 int64_t crwr_transition_nnz(crwr_handle h);
+/* Current kernel sizing (diagnostics): {H, limit, kmax, scap, warps/CTA, smem bytes/warp, grid, SMs}. */
+int32_t crwr_get_shape(crwr_handle h, int64_t* h_out8);
 
 /* Enqueue up to n_steps walk steps (utility.py:282-304).  Stop rules are evaluated on the
  * device; steps enqueued after the walk has stopped are no-ops.  Single-shard walks only. */

@@ -52,7 +52,7 @@ def test_workspace_bytes_validates_config_without_gpu():
 
 def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.Config) == 64
-    assert C.sizeof(_lib.StepRecord) == 40
+    assert C.sizeof(_lib.StepRecord) == 56
     assert C.sizeof(_lib.Status) == 56
 
 
