@@ -134,7 +134,8 @@ def next_row_hints(max_row_len: int, max_kept: int, perc: float, issued: int):
     if issued < 2:
         return 8 * max_row_len, max_row_len
     if issued < 3:
-        return max_row_len, int(max_row_len * min(1.0, 2.0 * (1.0 - perc / 100.0) + 0.05))
+        # first cut steps: rows may still grow a little; the kept share is not yet observed
+        return max_row_len + max_row_len // 4, int(max_row_len * min(1.0, 2.0 * (1.0 - perc / 100.0) + 0.05))
     return max_row_len, max_kept
 
 
@@ -323,8 +324,8 @@ class Walker:
         issued = 0
         hints = next_row_hints(0, 0, perc, 0)
         while True:
-            # early steps change shape quickly: poll after each; later run four at a time
-            chunk = 1 if issued < 4 else 4
+            # steps 0 and 1 change the row shapes most: poll after each; later run four at a time
+            chunk = 1 if issued < 2 else 4
             chunk = min(chunk, max_steps - issued)
             self.set_row_hints(*hints)
             _lib.check(lib.crwr_walk_enqueue(h, chunk, self._stream()))

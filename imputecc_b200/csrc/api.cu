@@ -8,8 +8,8 @@
 #include <cmath>
 
 #include "common.cuh"
-#include "propagate.cuh"
 #include "select.cuh"
+#include "propagate.cuh"
 #include "transition.cuh"
 #include "finish.cuh"
 
@@ -134,6 +134,8 @@ struct crwr_handle_s {
     int grid;                       // its persistent grid size
     int max_smem_optin;
     double rp, perc;
+    WalkState* h_state = nullptr;               // pinned host mirror of the device state (polls)
+    long long hint_len = -1, hint_kept = -1;    // last sizing hints (configure_shape is skipped when unchanged)
     bool profile = false;                       // CUDA events around every main propagate launch
     std::vector<cudaEvent_t> ev;                // start/end pairs
     template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
@@ -154,9 +156,10 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
     if (kmax < 64) kmax = 64;
     if (kmax > n) kmax = round_up(n, 32);
     const double avg_deg = h->p_nnz > 0 ? (double)h->p_nnz / (double)n : 8.0;
-    long long scap = round_up((long long)(32.0 * avg_deg * 1.15) + 32, 64);
+    // staging buffer: about 16 P rows per batch - enough rounds to cover the cp.async latency of the next one
+    long long scap = round_up((long long)(16.0 * avg_deg), 64);
     if (scap < 256) scap = 256;
-    if (scap > 4096) scap = 4096;
+    if (scap > 768) scap = 768;
     PropShape sh;
     for (;;) {
         long long H = round_up(limit + limit / 3 + 32, 32);
@@ -168,11 +171,11 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
         if (kmax > 1024 && kmax * 2 > limit) kmax = round_up(kmax / 2, 32);
         else limit = round_up(limit * 3 / 4, 32);
     }
-    int w = (int)(57344 / sh.per_warp);
+    int w = (int)((57344 - kHistWin * sizeof(unsigned int)) / sh.per_warp);
     if (w < 1) w = 1;
     if (w > 8) w = 8;
     sh.warps = w;
-    const size_t smem = sh.per_warp * (size_t)w;
+    const size_t smem = sh.per_warp * (size_t)w + kHistWin * sizeof(unsigned int);
     cudaError_t e = cudaFuncSetAttribute(propagate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
@@ -184,8 +187,10 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
     return 0;
 }
 
+unsigned long long* hist_ptr(crwr_handle_s* h);
+
 template <typename T>
-PropArgs<T> prop_args(crwr_handle_s* h, int parity) {
+PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     const Layout& L = h->L;
     PropArgs<T> a;
     a.p_indptr = h->at<int32_t>(L.p_indptr);
@@ -203,12 +208,14 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity) {
     a.row_begin = (int32_t)h->cfg.row_begin;
     a.scale = (T)(1.0 - h->rp);                 // (1 - rp) * matrix: the scalar takes the matrix dtype
     a.restart = (T)(float)h->rp;                // rp * I with I float32 (utility.py:278)
+    a.hist = fused ? hist_ptr(h) : nullptr;
+    a.fused_select = fused ? 1 : 0;
     return a;
 }
 
 template <typename T>
-int launch_propagate(crwr_handle_s* h, int parity, cudaStream_t st) {
-    PropArgs<T> a = prop_args<T>(h, parity);
+int launch_propagate(crwr_handle_s* h, int parity, bool fused, cudaStream_t st) {
+    PropArgs<T> a = prop_args<T>(h, parity, fused);
     const int rows = a.n_rows;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
@@ -220,7 +227,7 @@ int launch_propagate(crwr_handle_s* h, int parity, cudaStream_t st) {
         int grid = (rows + sh.warps - 1) / sh.warps;
         if (grid > h->grid) grid = h->grid;
         if (grid < 1) grid = 1;
-        propagate_kernel<T><<<grid, sh.warps * 32, sh.per_warp * (size_t)sh.warps, st>>>(a, sh);
+        propagate_kernel<T><<<grid, sh.warps * 32, sh.per_warp * (size_t)sh.warps + kHistWin * sizeof(unsigned int), st>>>(a, sh);
     }
     ++g_launches;
     if (h->profile) {
@@ -247,10 +254,10 @@ int launch_propagate(crwr_handle_s* h, int parity, cudaStream_t st) {
 unsigned long long* hist_ptr(crwr_handle_s* h) { return h->at<unsigned long long>(h->L.xbuf) + kXExtras; }
 
 template <typename T>
-int launch_hist(crwr_handle_s* h, int out_parity, int level, cudaStream_t st) {
+int launch_hist(crwr_handle_s* h, int out_parity, int level, int fused, cudaStream_t st) {
     const Layout& L = h->L;
     select_hist_kernel<T><<<h->sm_count, 512, 0, st>>>(h->at<T>(L.it_vals[out_parity]), h->at<WalkState>(L.state),
-                                                       hist_ptr(h), level);
+                                                       hist_ptr(h), level, fused);
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -261,17 +268,7 @@ int launch_scan(crwr_handle_s* h, int level, cudaStream_t st) {
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
-template <typename T>
-int launch_gather(crwr_handle_s* h, int out_parity, cudaStream_t st) {
-    const Layout& L = h->L;
-    select_gather_kernel<T><<<h->sm_count, 512, 0, st>>>(h->at<T>(L.it_vals[out_parity]), h->at<WalkState>(L.state),
-                                                         h->at<unsigned long long>(L.cand), (unsigned long long)L.cand_cap);
-    ++g_launches;
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
-// gathered: candidate blocks of all ranks (sharded) or null (own block only)
-template <typename T>
-int launch_finish(crwr_handle_s* h, int do_select, const void* gathered, cudaStream_t st) {
+FinishArgs finish_args(crwr_handle_s* h, int do_select, const void* gathered) {
     const Layout& L = h->L;
     FinishArgs a;
     a.st = h->at<WalkState>(L.state);
@@ -285,7 +282,22 @@ int launch_finish(crwr_handle_s* h, int do_select, const void* gathered, cudaStr
     a.cand_cap = (unsigned long long)L.cand_cap;
     a.trace = h->at<crwr_step_record>(L.trace);
     a.do_select = do_select;
-    finish_step_kernel<T><<<1, 1024, 0, st>>>(a);
+    return a;
+}
+
+template <typename T>
+int launch_gather(crwr_handle_s* h, int out_parity, int fused, cudaStream_t st) {
+    const Layout& L = h->L;
+    select_gather_kernel<T><<<h->sm_count, 512, 0, st>>>(h->at<T>(L.it_vals[out_parity]), h->at<WalkState>(L.state),
+                                                         h->at<unsigned long long>(L.cand), (unsigned long long)L.cand_cap,
+                                                         fused, finish_args(h, 1, nullptr));
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+// gathered: candidate blocks of all ranks (sharded) or null (own block only)
+template <typename T>
+int launch_finish(crwr_handle_s* h, int do_select, const void* gathered, cudaStream_t st) {
+    finish_step_kernel<T><<<1, 1024, 0, st>>>(finish_args(h, do_select, gathered));
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -296,15 +308,17 @@ int enqueue_step(crwr_handle_s* h, cudaStream_t st) {
     // runs completely or (after the stop rule fired) is skipped completely.
     const int step = h->steps_enqueued;
     const int parity = step & 1;
-    if (launch_propagate<T>(h, parity, st)) return -1;
-    if (step >= 1) {
-        if (launch_hist<T>(h, parity ^ 1, 0, st)) return -1;
-        if (launch_scan<T>(h, 0, st)) return -1;
-        if (launch_hist<T>(h, parity ^ 1, 1, st)) return -1;
-        if (launch_scan<T>(h, 1, st)) return -1;
-        if (launch_gather<T>(h, parity ^ 1, st)) return -1;
+    if (step == 0) {
+        // no percentile cut on step 0 (utility.py:286)
+        if (launch_propagate<T>(h, parity, false, st)) return -1;
+        if (launch_finish<T>(h, 0, nullptr, st)) return -1;
+    } else {
+        // propagate (+ level-0/1 histograms in its epilogue) -> large-row kernel (+ scans in its last CTA)
+        // -> level-1 histogram pass (skipped on the device when the prediction held) -> gather (+ finish)
+        if (launch_propagate<T>(h, parity, true, st)) return -1;
+        if (launch_hist<T>(h, parity ^ 1, 1, 1, st)) return -1;
+        if (launch_gather<T>(h, parity ^ 1, 1, st)) return -1;
     }
-    if (launch_finish<T>(h, step >= 1 ? 1 : 0, nullptr, st)) return -1;
     h->steps_enqueued = step + 1;
     return 0;
 }
@@ -413,6 +427,17 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     h->walking = false;
     h->steps_enqueued = 0;
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cudaMallocHost((void**)&h->h_state, sizeof(WalkState)) != cudaSuccess) {
+        delete h;
+        CRWR_FAIL(CRWR_ERR_CUDA, "cudaMallocHost failed");
+    }
+    // the large-row kernel's bitmaps clean up after themselves: zero them once
+    if (cudaMemset(h->ws + h->L.d_tbits, 0, 4 * (size_t)h->L.words * h->L.dense_warps) != cudaSuccess ||
+        cudaMemset(h->ws + h->L.d_kbits, 0, 4 * (size_t)h->L.words * h->L.dense_warps) != cudaSuccess) {
+        cudaFreeHost(h->h_state);
+        delete h;
+        CRWR_FAIL(CRWR_ERR_CUDA, "workspace memset failed");
+    }
     int e = cfg->dtype == CRWR_F64 ? configure_shape<double>(h, 192, 32) : configure_shape<float>(h, 192, 32);
     if (e) {
         delete h;
@@ -423,7 +448,10 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
 }
 
 int32_t crwr_destroy(crwr_handle h) {
-    if (h) for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    if (h) {
+        for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+        if (h->h_state) cudaFreeHost(h->h_state);
+    }
     delete h;
     return CRWR_OK;
 }
@@ -520,19 +548,10 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     cudaStream_t st = (cudaStream_t)stream;
     const Layout& L = h->L;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    WalkState s0;
-    memset(&s0, 0, sizeof(s0));
-    s0.rp = rp; s0.perc = perc; s0.tol = tol; s0.max_steps = max_steps;
-    CUDA_TRY(cudaMemcpyAsync(h->ws + L.state, &s0, sizeof(s0), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));   // s0 lives on this stack frame
-    CUDA_TRY(cudaMemsetAsync(h->ws + L.xbuf, 0, 8 * (size_t)(kXExtras + kSelectLevels * kSelectBins), st));
-    {
-        const unsigned long long hdr[2] = {0ull, ~0ull};
-        CUDA_TRY(cudaMemcpyAsync(h->ws + L.cand, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-    }
-    CUDA_TRY(cudaMemsetAsync(h->ws + L.d_tbits, 0, 4 * (size_t)L.words * L.dense_warps, st));
-    CUDA_TRY(cudaMemsetAsync(h->ws + L.d_kbits, 0, 4 * (size_t)L.words * L.dense_warps, st));
+    init_state_kernel<<<1, 256, 0, st>>>(h->at<WalkState>(L.state), rp, perc, tol, max_steps,
+                                         h->at<unsigned long long>(L.xbuf), kXExtras + kSelectLevels * kSelectBins,
+                                         h->at<unsigned long long>(L.cand));
+    LAUNCH_CHECK();
     const int rows = (int)(h->cfg.row_end - h->cfg.row_begin);
     if (h->cfg.dtype == CRWR_F64) {
         IterBuf<double> b{h->at<int32_t>(L.it_cols[0]), h->at<double>(L.it_vals[0]), h->at<long long>(L.it_ptr[0]),
@@ -576,10 +595,13 @@ int32_t crwr_profile_read(crwr_handle h, double* h_total_ms, int64_t* h_launches
 
 int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept) {
     if (!h || max_row_len < 0 || max_kept < 0) CRWR_FAIL(CRWR_ERR_INVALID, "bad row hints");
+    if (max_row_len == h->hint_len && max_kept == h->hint_kept) return CRWR_OK;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     int e = h->cfg.dtype == CRWR_F64 ? configure_shape<double>(h, max_row_len, max_kept)
                                      : configure_shape<float>(h, max_row_len, max_kept);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "kernel sizing failed: %s", cudaGetErrorString((cudaError_t)e));
+    h->hint_len = max_row_len;
+    h->hint_kept = max_kept;
     return CRWR_OK;
 }
 
@@ -614,7 +636,7 @@ int32_t crwr_walk_enqueue(crwr_handle h, int32_t n_steps, void* stream) {
 
 int32_t crwr_step_propagate(crwr_handle h, void* stream) {
     STEP_PROLOGUE();
-    int e = f64 ? launch_propagate<double>(h, parity, st) : launch_propagate<float>(h, parity, st);
+    int e = f64 ? launch_propagate<double>(h, parity, false, st) : launch_propagate<float>(h, parity, false, st);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "propagate launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     pack_exchange_kernel<<<1, 32, 0, st>>>(h->at<WalkState>(h->L.state), h->at<unsigned long long>(h->L.xbuf));
     LAUNCH_CHECK();
@@ -623,7 +645,7 @@ int32_t crwr_step_propagate(crwr_handle h, void* stream) {
 int32_t crwr_step_hist(crwr_handle h, int32_t level, void* stream) {
     STEP_PROLOGUE();
     if (level < 0 || level >= kSelectLevels) CRWR_FAIL(CRWR_ERR_INVALID, "level out of range");
-    int e = f64 ? launch_hist<double>(h, parity ^ 1, level, st) : launch_hist<float>(h, parity ^ 1, level, st);
+    int e = f64 ? launch_hist<double>(h, parity ^ 1, level, 0, st) : launch_hist<float>(h, parity ^ 1, level, 0, st);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "hist launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return CRWR_OK;
 }
@@ -636,7 +658,7 @@ int32_t crwr_step_scan(crwr_handle h, int32_t level, void* stream) {
 }
 int32_t crwr_step_gather(crwr_handle h, void* stream) {
     STEP_PROLOGUE();
-    int e = f64 ? launch_gather<double>(h, parity ^ 1, st) : launch_gather<float>(h, parity ^ 1, st);
+    int e = f64 ? launch_gather<double>(h, parity ^ 1, 0, st) : launch_gather<float>(h, parity ^ 1, 0, st);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "gather launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return CRWR_OK;
 }
@@ -670,9 +692,9 @@ int64_t crwr_exchange_bytes(crwr_handle h, int32_t which) {
 int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
     if (!h || !out) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    WalkState s;
-    CUDA_TRY(cudaMemcpyAsync(&s, h->ws + h->L.state, sizeof(s), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h->h_state, h->ws + h->L.state, sizeof(WalkState), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    const WalkState& s = *h->h_state;
     out->steps_done = s.step;
     out->stop_reason = s.done ? s.stop_reason : CRWR_STOP_RUNNING;
     out->capacity_overflow = s.capacity_overflow | (s.select_overflow << 1);

@@ -13,6 +13,7 @@ constexpr int kSelectLevels = 2;                // full-data histogram levels be
 constexpr int kCandSmem = 4096;                 // candidates ranked inside shared memory
 constexpr int kMaxTrace = 4096;                 // per-step records kept on the device
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kHistWin = 512;                   // level-0 bins kept in a per-CTA shared-memory window
 
 // ---------------------------------------------------------------------------------------------
 // Exact (non-contracted) arithmetic.  scipy's csr_matmat does `sums[j] += v * B[k,j]` as a
@@ -30,6 +31,12 @@ __device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
 __device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
 
 // Order-preserving map float -> unsigned (all finite values, either sign).
+// First level-0 bin of the per-CTA histogram window: 448 bins below bin(1.0), 64 at and above it
+// (float32: 2^-56 .. 2^8 at 8 bins per octave; float64: 2^-448 .. 2^64 at one bin per octave).
+template <typename T> struct HistWindow;
+template <> struct HistWindow<float> { static constexpr int base = (0xBF800000u >> 20) - 448; };
+template <> struct HistWindow<double> { static constexpr int base = 0xBFF - 448; };
+
 template <typename T> struct KeyOf;
 template <> struct KeyOf<float> {
     typedef uint32_t type;
@@ -96,6 +103,13 @@ struct WalkState {
     int32_t last_fallback_rows;
     double last_delta;
     unsigned long long sq_limb[3];  // sum of per-row ||dQ||^2 in 2^-64 fixed point, 32-bit limbs
+    // fused select (unsharded walks): histograms are filled by the propagate epilogue, scans and the
+    // finish step run in the last CTA of the following kernels
+    unsigned long long pred_prefix0;   // level-0 bin of the previous cut: level-1 histogram is pre-filled for it
+    int32_t pred_valid;                // pred_prefix0 is meaningful
+    int32_t hist1_ready;               // level-1 histogram already holds the counts of the selected level-0 bin
+    unsigned int tick_dense, tick_hist1, tick_gather;   // last-CTA tickets
+    unsigned int pad2;
 };
 
 // Exchange block 0 of a sharded walk: level-0 histogram followed by these extras (all uint64, SUM).

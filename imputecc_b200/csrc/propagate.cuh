@@ -18,6 +18,7 @@
 // [restart entry if it is a new column] followed by the columns in first-touch order.
 #pragma once
 #include "common.cuh"
+#include "select.cuh"
 
 namespace crwr {
 
@@ -34,6 +35,8 @@ struct PropArgs {
     int32_t row_begin;       // global index of local row 0 (= its restart column)
     T scale;                 // (T)(1 - rp)
     T restart;               // (T)(float)rp : rp * I is float32 in the reference (utility.py:278)
+    unsigned long long* hist;   // [2][4096] select histograms; null: do not fuse (sharded walk, step 0)
+    int32_t fused_select;       // 1: the last CTA of the large-row kernel scans the histograms
 };
 
 // Adds one row's share of ||Q - Q~||_F^2 to the step total as three 32-bit limbs of a 2^-64
@@ -49,6 +52,35 @@ __device__ __forceinline__ void add_rowsq(WalkState* st, double x) {
     atomicAdd(&st->sq_limb[2], (unsigned long long)hi);
     atomicAdd(&st->sq_limb[1], (unsigned long long)m1);
     atomicAdd(&st->sq_limb[0], (unsigned long long)m0);
+}
+
+// Fused level-0 histogram of the percentile select (and level 1 for the predicted level-0 bin).
+// Level 0: values are counted into a per-CTA shared-memory window of kHistWin bins (one ATOMS per
+// distinct bin among a chunk's 32 values) that is flushed once at the end of the kernel - global
+// same-address atomics cost ~8 ns each on the hot bins.  Level 1 only concerns ~5% of the values and
+// spreads them over 4096 addresses, so it goes to global memory directly.
+template <typename T>
+__device__ __forceinline__ void hist_values(unsigned long long* hist, unsigned int* win, bool valid, T v,
+                                            bool pred_valid, typename KeyOf<T>::type pred0) {
+    typedef KeyOf<T> KO;
+    const typename KO::type key = KO::enc(v);
+    const unsigned bin0 = valid ? (unsigned)(key >> (KO::bits - kSelectBits)) : (0x80000000u | lane_id());
+    const unsigned peers = __match_any_sync(kFull, bin0);
+    if (valid && (peers & lanemask_lt()) == 0u) {
+        const unsigned w = bin0 - (unsigned)HistWindow<T>::base;
+        if (w < (unsigned)kHistWin) atomicAdd(&win[w], (unsigned)__popc(peers));
+        else atomicAdd(&hist[bin0], (unsigned long long)__popc(peers));
+    }
+    if (valid && pred_valid && (key >> (KO::bits - kSelectBits)) == pred0)
+        atomicAdd(&hist[kSelectBins + ((unsigned)(key >> (KO::bits - 2 * kSelectBits)) & (kSelectBins - 1))], 1ull);
+}
+
+template <typename T>
+__device__ __forceinline__ void hist_window_flush(unsigned long long* hist, const unsigned int* win) {
+    for (int i = threadIdx.x; i < kHistWin; i += blockDim.x) {
+        const unsigned c = win[i];
+        if (c) atomicAdd(&hist[HistWindow<T>::base + i], (unsigned long long)c);
+    }
 }
 
 __device__ __forceinline__ uint32_t hash_col(int32_t j, int log_h) {
@@ -214,11 +246,15 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
     int32_t* scol = reinterpret_cast<int32_t*>(p); p += align16((size_t)2 * SCAP * 4);
     uint16_t* ord = reinterpret_cast<uint16_t*>(p);
 
+    unsigned int* win = reinterpret_cast<unsigned int*>(smem_raw + (size_t)sh.warps * sh.per_warp);
+    for (int i = threadIdx.x; i < kHistWin; i += blockDim.x) win[i] = 0u;
     for (int i = lane; i < HT; i += 32) tkey[i] = -1;
-    __syncwarp();
+    __syncthreads();
 
     const bool cut_on = a.st->cut_on != 0;
     const T cut = (T)a.st->cut;
+    const bool pred_valid = a.st->pred_valid != 0;
+    const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)a.st->pred_prefix0;
     unsigned long long kept_total = 0;
     const int32_t* __restrict__ pcols = a.p_cols;
     const T* __restrict__ pvals = a.p_vals;
@@ -432,19 +468,22 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
         for (int b = 0; b < count; b += 32) {
             const int i = b + lane;
             bool one = false;
+            T v = (T)0;
             if (i < count) {
                 const int slot = ord[i];
-                T v = mul_rn(a.scale, tval[slot]);
+                v = mul_rn(a.scale, tval[slot]);
                 if (slot == dslot) v = add_rn(v, a.restart);
                 tval[slot] = v;
                 s1 += (double)v * (double)v;
                 one = v != (T)0;
             }
             nz += __popc(__ballot_sync(kFull, one));
+            if (a.hist) hist_values<T>(a.hist, win, one, v, pred_valid, pred0);
         }
         if (diag_new) {
             if (lane == 0) s1 += (double)a.restart * (double)a.restart;
             if (a.restart != (T)0) nz += 1;
+            if (a.hist) hist_values<T>(a.hist, win, lane == 0 && a.restart != (T)0, a.restart, pred_valid, pred0);
         }
         __syncwarp();
         double s2 = 0.0;
@@ -482,6 +521,8 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
         __syncwarp();
     }
     if (lane == 0 && kept_total) atomicAdd(&a.st->nnz_in, kept_total);
+    __syncthreads();
+    if (a.hist) hist_window_flush<T>(a.hist, win);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -527,9 +568,11 @@ __device__ __forceinline__ void dense_accumulate_row_of_p(const PropArgs<T>& a, 
 
 template <typename T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T> a, DenseScratch<T> sc) {
+    __shared__ unsigned int win[kHistWin];
     if (a.st->done) return;
+    for (int i = threadIdx.x; i < kHistWin; i += WARPS * 32) win[i] = 0u;
+    __syncthreads();
     const unsigned n_fb = a.st->fb_count;
-    if (n_fb == 0) return;
     const int lane = lane_id();
     const long long gw = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);
     T* acc = sc.acc + gw * sc.n;
@@ -539,9 +582,12 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T>
     uint32_t* kbits = sc.kbits + gw * sc.words;
     const bool cut_on = a.st->cut_on != 0;
     const T cut = (T)a.st->cut;
+    const bool pred_valid = a.st->pred_valid != 0;
+    const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)a.st->pred_prefix0;
     unsigned long long kept_total = 0;
 
     for (;;) {
+        if (n_fb == 0) break;
         unsigned r = 0;
         if (lane == 0) r = atomicAdd(&a.st->fb_counter, 1u);
         r = __shfl_sync(kFull, r, 0);
@@ -605,19 +651,22 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T>
         for (int b = 0; b < count; b += 32) {
             int i = b + lane;
             bool one = false;
+            T v = (T)0;
             if (i < count) {
                 const int j = ord[i];
-                T v = mul_rn(a.scale, acc[j]);
+                v = mul_rn(a.scale, acc[j]);
                 if (j == dcol) v = add_rn(v, a.restart);
                 acc[j] = v;
                 s1 += (double)v * (double)v;
                 one = v != (T)0;
             }
             nz += __popc(__ballot_sync(kFull, one));
+            if (a.hist) hist_values<T>(a.hist, win, one, v, pred_valid, pred0);
         }
         if (diag_new) {
             if (lane == 0) s1 += (double)a.restart * (double)a.restart;
             if (a.restart != (T)0) nz += 1;
+            if (a.hist) hist_values<T>(a.hist, win, lane == 0 && a.restart != (T)0, a.restart, pred_valid, pred0);
         }
         __syncwarp();
         // old entries: every kept column has its bit in kbits and its value in oldv
@@ -652,6 +701,39 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T>
         __syncwarp();
     }
     if (lane == 0 && kept_total) atomicAdd(&a.st->nnz_in, kept_total);
+    __syncthreads();
+    if (a.hist && n_fb) hist_window_flush<T>(a.hist, win);
+
+    // ---- fused select (unsharded walk): every value of the step is now in the level-0 histogram; the
+    // last CTA locates the bin of the percentile and, when the level-1 histogram was pre-filled for that
+    // very bin (prediction from the previous cut), the 24-bit prefix as well.
+    if (a.fused_select && last_block(&a.st->tick_dense)) {
+        WalkState* st = a.st;
+        scan_level<T, WARPS * 32>(st, a.hist, 0);
+        const bool hit = st->pred_valid && st->prefix == st->pred_prefix0;
+        __syncthreads();
+        if (hit) {
+            scan_level<T, WARPS * 32>(st, a.hist, 1);
+            if (threadIdx.x == 0) st->hist1_ready = 1;
+        } else {
+            for (int i = threadIdx.x; i < kSelectBins; i += WARPS * 32) a.hist[kSelectBins + i] = 0ull;
+            if (threadIdx.x == 0) st->hist1_ready = 0;
+        }
+    }
+}
+
+// Walk state for step 0 (utility.py:275-280), exchange buffer cleared, candidate block header reset.
+__global__ void init_state_kernel(WalkState* st, double rp, double perc, double tol, int max_steps,
+                                  unsigned long long* xbuf, int xbuf_len, unsigned long long* cand_block) {
+    for (int i = threadIdx.x; i < xbuf_len; i += blockDim.x) xbuf[i] = 0ull;
+    if (threadIdx.x == 0) {
+        WalkState s;
+        memset(&s, 0, sizeof(s));
+        s.rp = rp; s.perc = perc; s.tol = tol; s.max_steps = max_steps;
+        *st = s;
+        cand_block[0] = 0ull;
+        cand_block[1] = ~0ull;
+    }
 }
 
 // Q0 = I (utility.py:279): every local row holds its restart column with value 1.

@@ -13,49 +13,33 @@
 
 namespace crwr {
 
-template <typename T>
-__global__ void __launch_bounds__(512) select_hist_kernel(const T* __restrict__ vals, WalkState* st,
-                                                          unsigned long long* __restrict__ hist, int level) {
-    typedef KeyOf<T> KO;
-    typedef typename KO::type K;
-    __shared__ unsigned int sh[kSelectBins];
-    if (st->done) return;
-    for (int i = threadIdx.x; i < kSelectBins; i += blockDim.x) sh[i] = 0u;
+// True in exactly one CTA of the grid: the last one to arrive.  All threads of every CTA call it.
+__device__ __forceinline__ bool last_block(unsigned int* ticket) {
+    __shared__ int s_last;
     __syncthreads();
-    const long long n = (long long)st->cursor;
-    const K prefix = (K)st->prefix;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const K key = KO::enc(vals[i]);
-        if (level == 0) {
-            atomicAdd(&sh[(unsigned)(key >> (KO::bits - kSelectBits))], 1u);
-        } else {
-            if ((key >> (KO::bits - kSelectBits)) == prefix)
-                atomicAdd(&sh[(unsigned)(key >> (KO::bits - 2 * kSelectBits)) & (kSelectBins - 1)], 1u);
-        }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
-    unsigned long long* out = hist + (size_t)level * kSelectBins;
-    for (int i = threadIdx.x; i < kSelectBins; i += blockDim.x) {
-        unsigned int c = sh[i];
-        if (c) atomicAdd(&out[i], (unsigned long long)c);
-    }
+    if (s_last) __threadfence();
+    return s_last != 0;
 }
 
-// Single CTA of 1024 threads.  hist already holds the GLOBAL counts of this level.
-template <typename T>
-__global__ void __launch_bounds__(1024) select_scan_kernel(WalkState* st, const unsigned long long* __restrict__ hist,
-                                                           int level) {
+// Block-wide (BLOCK threads): locate the bin of `hist[level]` that holds rank_k; level 0 first derives
+// n, the virtual index and gamma from the total count.  hist holds the GLOBAL counts of the level.
+template <typename T, int BLOCK>
+__device__ void scan_level(WalkState* st, const unsigned long long* hist, int level) {
+    constexpr int BPT = kSelectBins / BLOCK;
     __shared__ unsigned long long warp_tot[32];
     __shared__ unsigned long long s_total;
-    if (st->done) return;
     const unsigned long long* h = hist + (size_t)level * kSelectBins;
     const int t = threadIdx.x;
-    unsigned long long c[4];
+    unsigned long long c[BPT];
     unsigned long long mine = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { c[i] = h[t * 4 + i]; mine += c[i]; }
-    // inclusive scan of per-thread totals
+    for (int i = 0; i < BPT; ++i) { c[i] = __ldcg(h + t * BPT + i); mine += c[i]; }
     unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -65,14 +49,14 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(WalkState* st, const 
     if ((t & 31) == 31) warp_tot[t >> 5] = incl;
     __syncthreads();
     if (t < 32) {
-        unsigned long long w = warp_tot[t];
+        unsigned long long w = t < BLOCK / 32 ? warp_tot[t] : 0ull;
         unsigned long long wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long v = __shfl_up_sync(kFull, wi, o);
             if (t >= o) wi += v;
         }
-        warp_tot[t] = wi - w;   // exclusive
+        if (t < BLOCK / 32) warp_tot[t] = wi - w;   // exclusive
         if (t == 31) s_total = wi;
     }
     __syncthreads();
@@ -105,43 +89,15 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(WalkState* st, const 
     __syncthreads();                                            // all reads precede the single write
     unsigned long long run = excl;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < BPT; ++i) {
         if (target >= run && target < run + c[i]) {
             st->below = below0 + run;      // exactly one thread matches
-            st->prefix = (prefix0 << kSelectBits) | (unsigned long long)(t * 4 + i);
+            st->prefix = (prefix0 << kSelectBits) | (unsigned long long)(t * BPT + i);
             st->bin_count = c[i];
         }
         run += c[i];
     }
-}
-
-// Candidate block layout (uint64): [0] count, [1] smallest key above the candidate bin, [2..] keys.
-template <typename T>
-__global__ void __launch_bounds__(512) select_gather_kernel(const T* __restrict__ vals, WalkState* st,
-                                                            unsigned long long* __restrict__ block,
-                                                            unsigned long long cand_cap) {
-    typedef KeyOf<T> KO;
-    typedef typename KO::type K;
-    if (st->done) return;
-    const long long n = (long long)st->cursor;
-    const K prefix = (K)st->prefix;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    K best = ~(K)0;
-    bool have = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const K key = KO::enc(vals[i]);
-        const K p = key >> (KO::bits - 2 * kSelectBits);
-        if (p == prefix) {
-            unsigned long long idx = atomicAdd(&block[0], 1ull);
-            if (idx < cand_cap) block[kCandHeader + idx] = (unsigned long long)key;
-        } else if (p > prefix) {
-            if (!have || key < best) best = key;
-            have = true;
-        }
-    }
-    unsigned long long b64 = have ? (unsigned long long)best : ~0ull;
-    b64 = warp_min(b64);
-    if ((threadIdx.x & 31) == 0 && b64 != ~0ull) atomicMin(&block[1], b64);
+    __syncthreads();
 }
 
 // Block-wide radix select of local rank r among cand[0..c) (keys share their top 24 bits), 8 bits at
@@ -202,7 +158,7 @@ struct FinishArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(1024) finish_step_kernel(FinishArgs a) {
+__device__ void finish_step_body(const FinishArgs& a) {
     typedef KeyOf<T> KO;
     typedef typename KO::type K;
     __shared__ unsigned long long sk[kCandSmem];
@@ -212,7 +168,6 @@ __global__ void __launch_bounds__(1024) finish_step_kernel(FinishArgs a) {
     __shared__ unsigned long long s_xk, s_xk1, s_total, s_succ;
     __shared__ int s_have1, s_ovf;
     WalkState* st = a.st;
-    if (st->done) return;
     const int t = threadIdx.x;
 
     if (t == 0) { s_have1 = 0; s_xk = 0; s_xk1 = 0; s_ovf = 0; }
@@ -278,7 +233,7 @@ __global__ void __launch_bounds__(1024) finish_step_kernel(FinishArgs a) {
                 __syncthreads();
                 if (t == 0) {
                     unsigned long long b = ~0ull;
-                    for (int w = 0; w < 32; ++w) b = wbest[w] < b ? wbest[w] : b;
+                    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) b = wbest[w] < b ? wbest[w] : b;
                     s_xk = key;
                     if (below + dup < c) { s_xk1 = b; s_have1 = 1; }
                 }
@@ -365,11 +320,95 @@ __global__ void __launch_bounds__(1024) finish_step_kernel(FinishArgs a) {
         st->below = 0;
         st->prefix = 0;
         st->sq_limb[0] = 0; st->sq_limb[1] = 0; st->sq_limb[2] = 0;
+        st->tick_dense = 0; st->tick_hist1 = 0; st->tick_gather = 0;
+        st->hist1_ready = 0;
+        if (cut_applied) {      // the next cut most likely falls into the same level-0 bin
+            st->pred_prefix0 = (unsigned long long)(KO::enc((T)cut) >> (KO::bits - kSelectBits));
+            st->pred_valid = 1;
+        } else {
+            st->pred_valid = 0;
+        }
         a.own_block[0] = 0;
         a.own_block[1] = ~0ull;
     }
     __syncthreads();   // thread 0 has consumed the exchanged counters
     for (int i = t; i < kSelectLevels * kSelectBins + kXExtras; i += blockDim.x) a.hist[i] = 0ull;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) select_hist_kernel(const T* __restrict__ vals, WalkState* st,
+                                                          unsigned long long* __restrict__ hist, int level,
+                                                          int fused_tail) {
+    typedef KeyOf<T> KO;
+    typedef typename KO::type K;
+    __shared__ unsigned int sh[kSelectBins];
+    if (st->done) return;
+    if (fused_tail && st->hist1_ready) return;      // the propagate epilogue already filled and scanned this level
+    for (int i = threadIdx.x; i < kSelectBins; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    const long long n = (long long)st->cursor;
+    const K prefix = (K)st->prefix;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const K key = KO::enc(vals[i]);
+        if (level == 0) {
+            atomicAdd(&sh[(unsigned)(key >> (KO::bits - kSelectBits))], 1u);
+        } else {
+            if ((key >> (KO::bits - kSelectBits)) == prefix)
+                atomicAdd(&sh[(unsigned)(key >> (KO::bits - 2 * kSelectBits)) & (kSelectBins - 1)], 1u);
+        }
+    }
+    __syncthreads();
+    unsigned long long* out = hist + (size_t)level * kSelectBins;
+    for (int i = threadIdx.x; i < kSelectBins; i += blockDim.x) {
+        unsigned int c = sh[i];
+        if (c) atomicAdd(&out[i], (unsigned long long)c);
+    }
+    if (fused_tail && last_block(&st->tick_hist1)) scan_level<T, 512>(st, hist, level);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) select_scan_kernel(WalkState* st, const unsigned long long* __restrict__ hist,
+                                                           int level) {
+    if (st->done) return;
+    scan_level<T, 1024>(st, hist, level);
+}
+
+// Candidate block layout (uint64): [0] count, [1] smallest key above the candidate bin, [2..] keys.
+// fused_finish (unsharded walks): the last CTA to finish runs the step's finish logic.
+template <typename T>
+__global__ void __launch_bounds__(512) select_gather_kernel(const T* __restrict__ vals, WalkState* st,
+                                                            unsigned long long* __restrict__ block,
+                                                            unsigned long long cand_cap, int fused, FinishArgs fin) {
+    typedef KeyOf<T> KO;
+    typedef typename KO::type K;
+    if (st->done) return;
+    const long long n = (long long)st->cursor;
+    const K prefix = (K)st->prefix;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    K best = ~(K)0;
+    bool have = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const K key = KO::enc(vals[i]);
+        const K p = key >> (KO::bits - 2 * kSelectBits);
+        if (p == prefix) {
+            unsigned long long idx = atomicAdd(&block[0], 1ull);
+            if (idx < cand_cap) block[kCandHeader + idx] = (unsigned long long)key;
+        } else if (p > prefix) {
+            if (!have || key < best) best = key;
+            have = true;
+        }
+    }
+    unsigned long long b64 = have ? (unsigned long long)best : ~0ull;
+    b64 = warp_min(b64);
+    if ((threadIdx.x & 31) == 0 && b64 != ~0ull) atomicMin(&block[1], b64);
+    if (fused && last_block(&st->tick_gather)) finish_step_body<T>(fin);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) finish_step_kernel(FinishArgs a) {
+    if (a.st->done) return;
+    finish_step_body<T>(a);
 }
 
 // Sharded walk: publish this rank's step counters behind the level-0 histogram so that ONE

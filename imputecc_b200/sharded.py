@@ -105,7 +105,7 @@ def run_sharded_walk(phases, comm, perc, max_steps):
     issued = 0
     hints = next_row_hints(0, 0, perc, 0)
     while True:
-        chunk = 1 if issued < 4 else 4
+        chunk = 1 if issued < 2 else 4
         chunk = min(chunk, max_steps - issued)
         phases.set_row_hints(hints)
         for _ in range(chunk):

@@ -62,9 +62,9 @@ def contact_matrix(n_contigs: int, genome_size: int, intra_degree: int, inter_de
     cols = np.concatenate([v, v2])
     vals = np.concatenate([w, w2])
     keep = rows != cols
-    lo = np.minimum(rows[keep], cols[keep])
-    hi = np.maximum(rows[keep], cols[keep])
-    upper = sp.coo_matrix((vals[keep], (lo, hi)), shape=(n, n)).tocsr()   # duplicates summed
+    # A = coo -> csr (duplicates summed); A = triu(A, 1); A = A + A^T.  Pairs drawn
+    # with u > v fall below the diagonal and are discarded by triu, as in the survey's generator.
+    upper = sp.coo_matrix((vals[keep], (rows[keep], cols[keep])), shape=(n, n)).tocsr()
     upper = sp.triu(upper, 1).tocsr()
     full = (upper + upper.T).tocsr()
     full.sort_indices()
