@@ -475,7 +475,7 @@ def crwr_impute(normcc, marker_idx_sorted, rp, perc, tol: float = DEFAULT_TOL, m
     if group is not None:
         from .sharded import crwr_impute_sharded
         return crwr_impute_sharded(normcc, marker_idx_sorted, rp, perc, tol, max_steps, dtype, device, return_info, group)
-    M = sp.csr_matrix(normcc)
+    M = normcc if isinstance(normcc, sp.csr_matrix) else sp.csr_matrix(normcc)
     if not M.has_canonical_format:
         M = M.copy()
         M.sum_duplicates()

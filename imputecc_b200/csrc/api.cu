@@ -5,6 +5,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <mutex>
 #include <cmath>
 
 #include "common.cuh"
@@ -142,6 +143,26 @@ struct crwr_handle_s {
 };
 
 namespace {
+
+// Pinned host mirrors of the walk state are pooled: cudaMallocHost / cudaFreeHost cost about a
+// millisecond each, more than a whole small walk.
+std::vector<WalkState*> g_pinned_pool;
+std::mutex g_pinned_mutex;
+WalkState* acquire_pinned_state() {
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    if (!g_pinned_pool.empty()) {
+        WalkState* p = g_pinned_pool.back();
+        g_pinned_pool.pop_back();
+        return p;
+    }
+    WalkState* p = nullptr;
+    if (cudaMallocHost((void**)&p, sizeof(WalkState)) != cudaSuccess) return nullptr;
+    return p;
+}
+void release_pinned_state(WalkState* p) {
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    g_pinned_pool.push_back(p);
+}
 
 int round_up(long long x, int q) { return (int)(((x + q - 1) / q) * q); }
 
@@ -419,22 +440,24 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
         CRWR_FAIL(CRWR_ERR_INVALID, "workspace too small: need %lld bytes", (long long)h->L.bytes);
     }
     h->ws = (unsigned char*)d_workspace;
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
-    h->sm_count = prop.multiProcessorCount;
+    int sm_count = 0, smem_optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+    h->sm_count = sm_count;
     h->p_nnz = 0;
     h->have_p = false;
     h->walking = false;
     h->steps_enqueued = 0;
-    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-    if (cudaMallocHost((void**)&h->h_state, sizeof(WalkState)) != cudaSuccess) {
+    h->max_smem_optin = smem_optin;
+    h->h_state = acquire_pinned_state();
+    if (!h->h_state) {
         delete h;
         CRWR_FAIL(CRWR_ERR_CUDA, "cudaMallocHost failed");
     }
     // the large-row kernel's bitmaps clean up after themselves: zero them once
     if (cudaMemset(h->ws + h->L.d_tbits, 0, 4 * (size_t)h->L.words * h->L.dense_warps) != cudaSuccess ||
         cudaMemset(h->ws + h->L.d_kbits, 0, 4 * (size_t)h->L.words * h->L.dense_warps) != cudaSuccess) {
-        cudaFreeHost(h->h_state);
+        release_pinned_state(h->h_state);
         delete h;
         CRWR_FAIL(CRWR_ERR_CUDA, "workspace memset failed");
     }
@@ -450,7 +473,7 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
 int32_t crwr_destroy(crwr_handle h) {
     if (h) {
         for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
-        if (h->h_state) cudaFreeHost(h->h_state);
+        if (h->h_state) release_pinned_state(h->h_state);
     }
     delete h;
     return CRWR_OK;
