@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcrwr_b200.so")
+LIB_PATH = os.environ.get("CRWR_LIB", os.path.join(_HERE, "libcrwr_b200.so"))
 
 CRWR_F32, CRWR_F64 = 0, 1
 CRWR_OK, CRWR_ERR_INVALID, CRWR_ERR_CUDA, CRWR_ERR_CAPACITY, CRWR_ERR_STATE = 0, -1, -2, -3, -4

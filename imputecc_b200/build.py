@@ -30,8 +30,10 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
+    out = os.environ.get("CRWR_LIB_OUT", LIB)
+    extra = os.environ.get("CRWR_NVCC_FLAGS", "").split()
     cmd = [_nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xptxas", "-v", "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-Xptxas", "-v", "-Xcompiler", "-fPIC", "-shared", "-o", out] + extra + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     with open(os.path.join(HERE, "build.log"), "w") as fh:
@@ -40,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + log[-4000:])
     if verbose:
         print(log)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -137,6 +137,7 @@ struct crwr_handle_s {
     double rp, perc;
     WalkState* h_state = nullptr;               // pinned host mirror of the device state (polls)
     long long hint_len = -1, hint_kept = -1;    // last sizing hints (configure_shape is skipped when unchanged)
+    long long hint_len_eff = 128;               // expected longest product row
     bool profile = false;                       // CUDA events around every main propagate launch
     std::vector<cudaEvent_t> ev;                // start/end pairs
     template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
@@ -170,7 +171,7 @@ int round_up(long long x, int q) { return (int)(((x + q - 1) / q) * q); }
 template <typename T>
 int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept) {
     const long long n = h->cfg.n_contigs;
-    long long limit = round_up(max_row_len + max_row_len / 3 + 64, 32);
+    long long limit = round_up(max_row_len + max_row_len / 4 + 48, 32);
     if (limit < 256) limit = 256;
     if (limit > n + 32) limit = round_up(n + 32, 32);
     long long kmax = round_up(max_kept + max_kept / 4 + 32, 32);
@@ -179,7 +180,7 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
     const double avg_deg = h->p_nnz > 0 ? (double)h->p_nnz / (double)n : 8.0;
     // staging buffer: about 16 P rows per batch - enough rounds to cover the cp.async latency of the next one
     long long scap = round_up((long long)(16.0 * avg_deg), 64);
-    if (scap < 256) scap = 256;
+    if (scap < 128) scap = 128;
     if (scap > 768) scap = 768;
     PropShape sh;
     for (;;) {
@@ -231,6 +232,19 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     a.restart = (T)(float)h->rp;                // rp * I with I float32 (utility.py:278)
     a.hist = fused ? hist_ptr(h) : nullptr;
     a.fused_select = fused ? 1 : 0;
+    // a warp reserves output space for a few rows at a time (zero-padded leftovers are skipped by the select)
+    {
+        long long ch = 3 * (long long)h->hint_len_eff;
+        if (ch < 256) ch = 256;
+        if (ch > 8192) ch = 8192;
+        a.chunk = (int32_t)ch;
+        // rows per scheduling request: one while every warp gets at most a few rows, more when there are many
+        const long long warps = (long long)h->grid * h->shape.warps;
+        long long rc = a.n_rows / (warps * 2 > 0 ? warps * 2 : 1);
+        rc = 1;      // measured: one row per request is fastest at every size (2 and 4 lose to imbalance)
+        if (const char* e = getenv("CRWR_ROW_CHUNK")) rc = atoi(e) > 0 ? atoi(e) : rc;
+        a.row_chunk = (int32_t)rc;
+    }
     return a;
 }
 
@@ -625,6 +639,7 @@ int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept)
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "kernel sizing failed: %s", cudaGetErrorString((cudaError_t)e));
     h->hint_len = max_row_len;
     h->hint_kept = max_kept;
+    h->hint_len_eff = max_row_len;
     return CRWR_OK;
 }
 
@@ -722,7 +737,7 @@ int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
     out->stop_reason = s.done ? s.stop_reason : CRWR_STOP_RUNNING;
     out->capacity_overflow = s.capacity_overflow | (s.select_overflow << 1);
     out->fallback_rows = s.last_fallback_rows;
-    out->nnz_iterate = (int64_t)s.cursor;
+    out->nnz_iterate = (int64_t)s.nnz_exact;
     out->max_row_len = s.last_max_row_len;
     out->max_kept = s.last_max_kept;
     out->last_cut = s.cut;

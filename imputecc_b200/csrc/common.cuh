@@ -82,6 +82,7 @@ struct WalkState {
     // per-step counters, reset by the finish kernel
     unsigned long long cursor;      // entries allocated in the output buffer (= local nnz_new)
     unsigned long long nnz_in;      // kept entries read this step (local)
+    unsigned long long nnz_exact;   // stored (non-zero) entries of the step's product (cursor may include zero padding)
     unsigned int row_counter;       // dynamic row scheduler of the main propagate kernel
     unsigned int fb_counter;        // ... of the large-row kernel
     unsigned int fb_count;          // rows queued for the large-row kernel
@@ -109,7 +110,9 @@ struct WalkState {
     int32_t pred_valid;                // pred_prefix0 is meaningful
     int32_t hist1_ready;               // level-1 histogram already holds the counts of the selected level-0 bin
     unsigned int tick_dense, tick_hist1, tick_gather;   // last-CTA tickets
-    unsigned int pad2;
+    unsigned int tick_prop;
+    int32_t scan_done;                 // the level scans of this step already ran (in the propagate kernel's last CTA)
+    int32_t pad3;
 };
 
 // Exchange block 0 of a sharded walk: level-0 histogram followed by these extras (all uint64, SUM).

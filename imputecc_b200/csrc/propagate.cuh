@@ -37,21 +37,149 @@ struct PropArgs {
     T restart;               // (T)(float)rp : rp * I is float32 in the reference (utility.py:278)
     unsigned long long* hist;   // [2][4096] select histograms; null: do not fuse (sharded walk, step 0)
     int32_t fused_select;       // 1: the last CTA of the large-row kernel scans the histograms
+    int32_t chunk;              // entries a warp reserves from the product buffer at a time
+    int32_t row_chunk;          // rows a warp takes from the row counter at a time
 };
 
-// Adds one row's share of ||Q - Q~||_F^2 to the step total as three 32-bit limbs of a 2^-64
-// fixed-point number.  Integer sums commute, so delta is bit-identical whatever the order in
-// which rows finish and however the rows are sharded over GPUs.
-__device__ __forceinline__ void add_rowsq(WalkState* st, double x) {
+// Fused select, unsharded walk: once every value of the step is in the level-0 histogram, one CTA locates
+// the level-0 bin of the percentile and, when the level-1 histogram was pre-filled for that very bin
+// (prediction from the previous cut), the 24-bit prefix as well; otherwise level 1 is cleared for the
+// histogram pass that follows.  Called by all BLOCK threads of the last CTA.
+template <typename T, int BLOCK>
+__device__ __noinline__ void scan_tail(WalkState* st, unsigned long long* hist) {
+    scan_level<T, BLOCK>(st, hist, 0);
+    const bool hit = st->pred_valid && st->prefix == st->pred_prefix0;
+    __syncthreads();
+    if (hit) {
+        scan_level<T, BLOCK>(st, hist, 1);
+        if (threadIdx.x == 0) { st->hist1_ready = 1; st->scan_done = 1; }
+    } else {
+        for (int i = threadIdx.x; i < kSelectBins; i += BLOCK) hist[kSelectBins + i] = 0ull;
+        if (threadIdx.x == 0) { st->hist1_ready = 0; st->scan_done = 1; }
+    }
+}
+
+// Per-warp running totals of a launch.  Everything a row contributes to the walk state is summed here
+// (identical values in all lanes) and published with a handful of atomics when the warp retires:
+// same-address atomics from every row serialise in L2 and were the bottleneck of small-row workloads.
+struct WarpTotals {
+    unsigned long long sq0, sq1, sq2;   // ||dQ||^2 as three 32-bit limbs of a 2^-64 fixed-point number
+    unsigned long long nnz_exact, kept;
+    int max_kept, max_row_len;
+    // output space: a private chunk of the product buffer, refilled from the global cursor
+    long long ch_base;
+    int ch_left;
+    bool ovf;
+};
+
+__device__ __forceinline__ void totals_init(WarpTotals& w) {
+    w.sq0 = w.sq1 = w.sq2 = w.nnz_exact = w.kept = 0ull;
+    w.max_kept = w.max_row_len = 0;
+    w.ch_base = 0; w.ch_left = 0; w.ovf = false;
+}
+
+// Integer limbs commute, so delta is bit-identical whatever the order in which rows finish and however
+// the rows are sharded over GPUs.
+__device__ __forceinline__ void totals_add_rowsq(WarpTotals& w, double x) {
     if (!(x > 0.0)) return;
     if (x >= 4294967296.0) x = 4294967295.0;
     const double hi = floor(x);
     const double f1 = (x - hi) * 4294967296.0;
     const double m1 = floor(f1);
     const double m0 = floor((f1 - m1) * 4294967296.0);
-    atomicAdd(&st->sq_limb[2], (unsigned long long)hi);
-    atomicAdd(&st->sq_limb[1], (unsigned long long)m1);
-    atomicAdd(&st->sq_limb[0], (unsigned long long)m0);
+    w.sq2 += (unsigned long long)hi;
+    w.sq1 += (unsigned long long)m1;
+    w.sq0 += (unsigned long long)m0;
+}
+
+template <typename T>
+__device__ __forceinline__ void pad_zero(const IterBuf<T>& out, long long base, int n) {
+    for (int i = lane_id(); i < n; i += 32) { out.cols[base + i] = -1; out.vals[base + i] = (T)0; }
+}
+
+// Reserves n entries of the product buffer for a row (uniform across the warp).  Space comes from the
+// warp's private chunk; an exhausted chunk is zero-padded (every pass over the value array ignores
+// zeros: a stored value is never zero) and replaced through ONE atomic on the global cursor.
+template <typename T>
+__device__ __forceinline__ long long reserve_row(const PropArgs<T>& a, WarpTotals& w, int n) {
+    if (n > w.ch_left) {
+        if (w.ch_left > 0 && !w.ovf) pad_zero(a.out, w.ch_base, w.ch_left);
+        const int sz = n > a.chunk ? n : a.chunk;
+        long long base = 0;
+        if (lane_id() == 0) base = (long long)atomicAdd(&a.st->cursor, (unsigned long long)sz);
+        base = __shfl_sync(kFull, base, 0);
+        w.ch_base = base;
+        w.ch_left = sz;
+        if (base + sz > a.out_cap) {
+            w.ovf = true;
+            if (lane_id() == 0) a.st->capacity_overflow = 1;
+        }
+    }
+    const long long r = w.ch_base;
+    w.ch_base += n;
+    w.ch_left -= n;
+    return r;
+}
+
+// Writes one finished row into its reserved space.  `emit(i, &col, &val)` yields the i-th candidate
+// (i < n_cand) in output order; zero values are dropped (csr_matmat / csr_plus_csr never store them) and
+// the unused tail of the reservation is zero-padded.
+template <typename T, typename Emit>
+__device__ __forceinline__ void write_row(const PropArgs<T>& a, WarpTotals& w, int row, long long base, int n_cand,
+                                          int n_nonzero, Emit emit) {
+    const int lane = lane_id();
+    const bool fits = !w.ovf;
+    if (lane == 0) {
+        a.out.row_ptr[row] = fits ? base : 0;
+        a.out.row_len[row] = fits ? n_nonzero : 0;
+    }
+    w.max_row_len = max(w.max_row_len, n_nonzero);
+    w.nnz_exact += (unsigned long long)n_nonzero;
+    if (!fits) return;
+    int written = 0;
+    for (int b = 0; b < n_cand; b += 32) {
+        int i = b + lane;
+        int32_t c = 0;
+        T v = (T)0;
+        if (i < n_cand) emit(i, c, v);
+        bool nz = (i < n_cand) && (v != (T)0);
+        unsigned m = __ballot_sync(kFull, nz);
+        if (nz) {
+            long long o = base + written + __popc(m & lanemask_lt());
+            a.out.cols[o] = c;
+            a.out.vals[o] = v;
+        }
+        written += __popc(m);
+    }
+    if (written < n_cand) pad_zero(a.out, base + written, n_cand - written);
+}
+
+// Retires a warp: pads its unused chunk and publishes its totals.
+template <typename T>
+__device__ __forceinline__ void totals_flush(const PropArgs<T>& a, WarpTotals& w) {
+    if (w.ch_left > 0 && !w.ovf) pad_zero(a.out, w.ch_base, w.ch_left);
+    if (lane_id() == 0) {
+        WalkState* st = a.st;
+        if (w.sq0) atomicAdd(&st->sq_limb[0], w.sq0);
+        if (w.sq1) atomicAdd(&st->sq_limb[1], w.sq1);
+        if (w.sq2) atomicAdd(&st->sq_limb[2], w.sq2);
+        if (w.nnz_exact) atomicAdd(&st->nnz_exact, w.nnz_exact);
+        if (w.kept) atomicAdd(&st->nnz_in, w.kept);
+        if (w.max_kept) atomicMax(&st->max_kept, w.max_kept);
+        if (w.max_row_len) atomicMax(&st->max_row_len, w.max_row_len);
+    }
+}
+
+// Rows are handed out `chunk` at a time by an atomic counter.
+__device__ __forceinline__ bool next_row(unsigned int* counter, int n_rows, int chunk, int& cur, int& lim) {
+    if (cur == lim) {
+        int r = 0;
+        if (lane_id() == 0) r = (int)atomicAdd(counter, (unsigned)chunk);
+        r = __shfl_sync(kFull, r, 0);
+        cur = r;
+        lim = min(r + chunk, n_rows);
+    }
+    return cur < n_rows;
 }
 
 // Fused level-0 histogram of the percentile select (and level 1 for the predicted level-0 bin).
@@ -87,20 +215,30 @@ __device__ __forceinline__ uint32_t hash_col(int32_t j, int log_h) {
     return ((uint32_t)j * 0x9E3779B1u) >> (32 - log_h);
 }
 
-// Writes one finished row.  `emit(i, &col, &val)` yields the i-th candidate (i < n_cand) in output
-// order; zero values are dropped.  Returns nothing; updates cursor / row tables / overflow flag.
-template <typename T, typename Emit>
-__device__ __forceinline__ void write_row(const PropArgs<T>& a, int row, int n_cand, int n_nonzero, Emit emit) {
-    const int lane = lane_id();
+// Output space for a row is reserved as soon as its candidate count is known (lane 0 issues the atomic;
+// the result is only broadcast when the row is written, so the round trip overlaps the epilogue).
+__device__ __forceinline__ long long reserve_row(WalkState* st, int n_cand) {
     long long base = 0;
-    if (lane == 0) base = (long long)atomicAdd(&a.st->cursor, (unsigned long long)n_nonzero);
-    base = __shfl_sync(kFull, base, 0);
-    const bool fits = base + n_nonzero <= a.out_cap;
+    if (lane_id() == 0) base = (long long)atomicAdd(&st->cursor, (unsigned long long)n_cand);
+    return base;      // valid in lane 0 only
+}
+
+// Writes one finished row into its reserved space.  `emit(i, &col, &val)` yields the i-th candidate
+// (i < n_cand) in output order; zero values are dropped (csr_matmat / csr_plus_csr never store them) and
+// the unused tail of the reservation is padded with zeros, which every later pass over the value array
+// ignores (a stored value is never zero).
+template <typename T, typename Emit>
+__device__ __forceinline__ void write_row(const PropArgs<T>& a, int row, long long base_lane0, int n_cand, int n_nonzero,
+                                          Emit emit) {
+    const int lane = lane_id();
+    const long long base = __shfl_sync(kFull, base_lane0, 0);
+    const bool fits = base + n_cand <= a.out_cap;
     if (lane == 0) {
         a.out.row_ptr[row] = fits ? base : 0;
         a.out.row_len[row] = fits ? n_nonzero : 0;
         if (!fits) a.st->capacity_overflow = 1;
         atomicMax(&a.st->max_row_len, n_nonzero);
+        atomicAdd(&a.st->nnz_exact, (unsigned long long)n_nonzero);
     }
     if (!fits) return;
     int written = 0;
@@ -118,6 +256,7 @@ __device__ __forceinline__ void write_row(const PropArgs<T>& a, int row, int n_c
         }
         written += __popc(m);
     }
+    for (int i = written + lane; i < n_cand; i += 32) { a.out.cols[base + i] = -1; a.out.vals[base + i] = (T)0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -255,7 +394,6 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
     const T cut = (T)a.st->cut;
     const bool pred_valid = a.st->pred_valid != 0;
     const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)a.st->pred_prefix0;
-    unsigned long long kept_total = 0;
     const int32_t* __restrict__ pcols = a.p_cols;
     const T* __restrict__ pvals = a.p_vals;
 
@@ -310,11 +448,12 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
         return nb;
     };
 
+    WarpTotals wt;
+    totals_init(wt);
+    int row_cur = 0, row_lim = 0;
     for (;;) {
-        int row = 0;
-        if (lane == 0) row = (int)atomicAdd(&a.st->row_counter, 1u);
-        row = __shfl_sync(kFull, row, 0);
-        if (row >= a.n_rows) break;
+        if (!next_row(&a.st->row_counter, a.n_rows, a.row_chunk, row_cur, row_lim)) break;
+        const int row = row_cur++;
 
         // ---- read the row, dropping entries at or below the previous cut (strict >, utility.py:290)
         const long long ptr = a.in.row_ptr[row];
@@ -342,7 +481,7 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
             }
         }
         __syncwarp();
-        if (lane == 0) atomicMax(&a.st->max_kept, nk);
+        wt.max_kept = max(wt.max_kept, nk);
         bool defer = nk > KMAX;
         int count = 0;
         if (!defer) {
@@ -445,7 +584,7 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
             if (lane == 0) a.fb_rows[atomicAdd(&a.st->fb_count, 1u)] = row;
             continue;
         }
-        kept_total += (unsigned long long)nk;
+        wt.kept += (unsigned long long)nk;
 
         // ---- epilogue: scale, restart add, norm, write
         const int32_t dcol = a.row_begin + row;
@@ -463,6 +602,8 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
             }
         }
         const bool diag_new = dslot < 0;
+        const int n_cand = count + (diag_new ? 1 : 0);
+        const long long base = reserve_row(a, wt, n_cand);
         double s1 = 0.0;
         int nz = 0;
         for (int b = 0; b < count; b += 32) {
@@ -507,12 +648,10 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
             const T d = sub_rn(oldv, newv);
             s2 += (double)d * (double)d - (double)newv * (double)newv;
         }
-        const double tot = warp_sum(s1 + s2);
-        if (lane == 0) add_rowsq(a.st, tot);
+        totals_add_rowsq(wt, warp_sum(s1 + s2));
 
-        const int n_cand = count + (diag_new ? 1 : 0);
         const int shift = diag_new ? 1 : 0;
-        write_row(a, row, n_cand, nz, [&](int i, int32_t& c, T& v) {
+        write_row(a, wt, row, base, n_cand, nz, [&](int i, int32_t& c, T& v) {
             if (i < shift) { c = dcol; v = a.restart; }
             else { const int slot = ord[i - shift]; c = tkey[slot]; v = tval[slot]; }
         });
@@ -520,7 +659,7 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
         for (int i = lane; i < count; i += 32) tkey[ord[i]] = -1;
         __syncwarp();
     }
-    if (lane == 0 && kept_total) atomicAdd(&a.st->nnz_in, kept_total);
+    totals_flush(a, wt);
     __syncthreads();
     if (a.hist) hist_window_flush<T>(a.hist, win);
 }
@@ -570,6 +709,7 @@ template <typename T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T> a, DenseScratch<T> sc) {
     __shared__ unsigned int win[kHistWin];
     if (a.st->done) return;
+    if (a.st->fb_count == 0 && !a.fused_select) return;
     for (int i = threadIdx.x; i < kHistWin; i += WARPS * 32) win[i] = 0u;
     __syncthreads();
     const unsigned n_fb = a.st->fb_count;
@@ -584,7 +724,8 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T>
     const T cut = (T)a.st->cut;
     const bool pred_valid = a.st->pred_valid != 0;
     const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)a.st->pred_prefix0;
-    unsigned long long kept_total = 0;
+    WarpTotals wt;
+    totals_init(wt);
 
     for (;;) {
         if (n_fb == 0) break;
@@ -640,8 +781,8 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T>
                 }
             }
         }
-        kept_total += (unsigned long long)nk;
-        if (lane == 0) atomicMax(&a.st->max_kept, nk);
+        wt.kept += (unsigned long long)nk;
+        wt.max_kept = max(wt.max_kept, nk);
         __syncwarp();
 
         const int32_t dcol = a.row_begin + row;
@@ -685,12 +826,12 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T>
                 }
             }
         }
-        const double tot = warp_sum(s1 + s2);
-        if (lane == 0) add_rowsq(a.st, tot);
+        totals_add_rowsq(wt, warp_sum(s1 + s2));
 
         const int n_cand = count + (diag_new ? 1 : 0);
         const int shift = diag_new ? 1 : 0;
-        write_row(a, row, n_cand, nz, [&](int i, int32_t& c, T& v) {
+        const long long base = reserve_row(a, wt, n_cand);
+        write_row(a, wt, row, base, n_cand, nz, [&](int i, int32_t& c, T& v) {
             if (i < shift) { c = dcol; v = a.restart; }
             else { c = ord[i - shift]; v = acc[c]; }
         });
@@ -700,26 +841,12 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T>
         for (int b = lane; b < len; b += 32) kbits[a.in.cols[ptr + b] >> 5] = 0u;
         __syncwarp();
     }
-    if (lane == 0 && kept_total) atomicAdd(&a.st->nnz_in, kept_total);
+    totals_flush(a, wt);
     __syncthreads();
     if (a.hist && n_fb) hist_window_flush<T>(a.hist, win);
 
-    // ---- fused select (unsharded walk): every value of the step is now in the level-0 histogram; the
-    // last CTA locates the bin of the percentile and, when the level-1 histogram was pre-filled for that
-    // very bin (prediction from the previous cut), the 24-bit prefix as well.
-    if (a.fused_select && last_block(&a.st->tick_dense)) {
-        WalkState* st = a.st;
-        scan_level<T, WARPS * 32>(st, a.hist, 0);
-        const bool hit = st->pred_valid && st->prefix == st->pred_prefix0;
-        __syncthreads();
-        if (hit) {
-            scan_level<T, WARPS * 32>(st, a.hist, 1);
-            if (threadIdx.x == 0) st->hist1_ready = 1;
-        } else {
-            for (int i = threadIdx.x; i < kSelectBins; i += WARPS * 32) a.hist[kSelectBins + i] = 0ull;
-            if (threadIdx.x == 0) st->hist1_ready = 0;
-        }
-    }
+    // ---- fused select (unsharded walk) when rows were deferred: the histogram is complete only now
+    if (a.fused_select && !a.st->scan_done && last_block(&a.st->tick_dense)) scan_tail<T, WARPS * 32>(a.st, a.hist);
 }
 
 // Walk state for step 0 (utility.py:275-280), exchange buffer cleared, candidate block header reset.

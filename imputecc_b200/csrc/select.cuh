@@ -30,16 +30,15 @@ __device__ __forceinline__ bool last_block(unsigned int* ticket) {
 // Block-wide (BLOCK threads): locate the bin of `hist[level]` that holds rank_k; level 0 first derives
 // n, the virtual index and gamma from the total count.  hist holds the GLOBAL counts of the level.
 template <typename T, int BLOCK>
-__device__ void scan_level(WalkState* st, const unsigned long long* hist, int level) {
+__device__ __noinline__ void scan_level(WalkState* st, const unsigned long long* hist, int level) {
     constexpr int BPT = kSelectBins / BLOCK;
     __shared__ unsigned long long warp_tot[32];
     __shared__ unsigned long long s_total;
     const unsigned long long* h = hist + (size_t)level * kSelectBins;
     const int t = threadIdx.x;
-    unsigned long long c[BPT];
     unsigned long long mine = 0;
-#pragma unroll
-    for (int i = 0; i < BPT; ++i) { c[i] = __ldcg(h + t * BPT + i); mine += c[i]; }
+#pragma unroll 8
+    for (int i = 0; i < BPT; ++i) mine += __ldcg(h + t * BPT + i);
     unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -87,15 +86,18 @@ __device__ void scan_level(WalkState* st, const unsigned long long* hist, int le
     const unsigned long long prefix0 = st->prefix;
     const unsigned long long target = st->rank_k - below0;      // rank inside the current bin set
     __syncthreads();                                            // all reads precede the single write
-    unsigned long long run = excl;
-#pragma unroll
-    for (int i = 0; i < BPT; ++i) {
-        if (target >= run && target < run + c[i]) {
-            st->below = below0 + run;      // exactly one thread matches
-            st->prefix = (prefix0 << kSelectBits) | (unsigned long long)(t * BPT + i);
-            st->bin_count = c[i];
+    if (target >= excl && target < excl + mine) {          // exactly one thread: the bin lies in its range
+        unsigned long long run = excl;
+        for (int i = 0; i < BPT; ++i) {
+            const unsigned long long c = __ldcg(h + t * BPT + i);
+            if (target < run + c) {
+                st->below = below0 + run;
+                st->prefix = (prefix0 << kSelectBits) | (unsigned long long)(t * BPT + i);
+                st->bin_count = c;
+                break;
+            }
+            run += c;
         }
-        run += c[i];
     }
     __syncthreads();
 }
@@ -265,7 +267,7 @@ __device__ void finish_step_body(const FinishArgs& a) {
             cap_ovf = a.xch[kXCapOvf]; sel_ovf = a.xch[kXSelOvf]; fb = a.xch[kXFallback];
         } else {
             l0 = st->sq_limb[0]; l1 = st->sq_limb[1]; l2 = st->sq_limb[2];
-            nnz_in = st->nnz_in; nnz_new = st->cursor;
+            nnz_in = st->nnz_in; nnz_new = st->nnz_exact;
             cap_ovf = (unsigned long long)st->capacity_overflow; sel_ovf = 0; fb = st->fb_count;
         }
         if (sel_ovf) st->select_overflow = 1;
@@ -311,6 +313,7 @@ __device__ void finish_step_body(const FinishArgs& a) {
         if (!done) {
             // counters of the next step (when stopping, cursor/max_row_len keep describing the result)
             st->cursor = 0;
+            st->nnz_exact = 0;
             st->max_row_len = 0;
         }
         st->nnz_in = 0;
@@ -320,7 +323,8 @@ __device__ void finish_step_body(const FinishArgs& a) {
         st->below = 0;
         st->prefix = 0;
         st->sq_limb[0] = 0; st->sq_limb[1] = 0; st->sq_limb[2] = 0;
-        st->tick_dense = 0; st->tick_hist1 = 0; st->tick_gather = 0;
+        st->tick_dense = 0; st->tick_hist1 = 0; st->tick_gather = 0; st->tick_prop = 0;
+        st->scan_done = 0;
         st->hist1_ready = 0;
         if (cut_applied) {      // the next cut most likely falls into the same level-0 bin
             st->pred_prefix0 = (unsigned long long)(KO::enc((T)cut) >> (KO::bits - kSelectBits));
@@ -350,7 +354,9 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const T* __restrict__ 
     const K prefix = (K)st->prefix;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const K key = KO::enc(vals[i]);
+        const T v = vals[i];
+        if (v == (T)0) continue;                      // zero padding of a row reservation
+        const K key = KO::enc(v);
         if (level == 0) {
             atomicAdd(&sh[(unsigned)(key >> (KO::bits - kSelectBits))], 1u);
         } else {
@@ -389,7 +395,9 @@ __global__ void __launch_bounds__(512) select_gather_kernel(const T* __restrict_
     K best = ~(K)0;
     bool have = false;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const K key = KO::enc(vals[i]);
+        const T v = vals[i];
+        if (v == (T)0) continue;                      // zero padding of a row reservation
+        const K key = KO::enc(v);
         const K p = key >> (KO::bits - 2 * kSelectBits);
         if (p == prefix) {
             unsigned long long idx = atomicAdd(&block[0], 1ull);
@@ -420,7 +428,7 @@ __global__ void pack_exchange_kernel(WalkState* st, unsigned long long* extras) 
         extras[kXSq1] = st->sq_limb[1];
         extras[kXSq2] = st->sq_limb[2];
         extras[kXNnzIn] = st->nnz_in;
-        extras[kXNnzNew] = st->cursor;
+        extras[kXNnzNew] = st->nnz_exact;
         extras[kXCapOvf] = (unsigned long long)st->capacity_overflow;
         extras[kXSelOvf] = (unsigned long long)st->select_overflow;
         extras[kXFallback] = st->fb_count;
