@@ -77,8 +77,11 @@ def markers_first_order(n_contigs: int, marker_idx_sorted) -> np.ndarray:
     return new_of_old
 
 
-def validate_inputs(normcc, marker_idx_sorted, rp, perc):
-    """Argument checks of the boundary (SURVEY.md §8b error conventions)."""
+def validate_inputs(normcc, marker_idx_sorted, rp, perc, check_values=True):
+    """Argument checks of the boundary (SURVEY.md §8b error conventions).
+
+    ``check_values=False`` leaves the scan for negative / non-finite contacts to the device
+    (crwr_build_transition reports it), saving a host pass over the matrix."""
     if not sp.issparse(normcc):
         raise ValueError("normcc must be a scipy sparse matrix")
     if normcc.shape[0] != normcc.shape[1]:
@@ -94,9 +97,10 @@ def validate_inputs(normcc, marker_idx_sorted, rp, perc):
         raise ValueError("rp must be in [0, 1]")
     if not (0.0 <= float(perc) <= 100.0):
         raise ValueError("Percentiles must be in the range [0, 100]")
-    data = normcc.data
-    if data.size and (not np.all(np.isfinite(data)) or data.min() < 0):
-        raise ValueError("contact values must be finite and non-negative")
+    if check_values:
+        data = normcc.data
+        if data.size and (not np.all(np.isfinite(data)) or data.min() < 0):
+            raise ValueError("contact values must be finite and non-negative")
 
 
 def shard_rows(n_rows: int, n_shards: int, weights: Optional[np.ndarray] = None) -> List[tuple]:
@@ -471,7 +475,7 @@ def crwr_impute(normcc, marker_idx_sorted, rp, perc, tol: float = DEFAULT_TOL, m
     walk dtype (the caller applies ``.tolil()`` as imputation.py:129 does).  With a
     ``torch.distributed`` process group the restart rows are sharded over its ranks.
     """
-    validate_inputs(normcc, marker_idx_sorted, rp, perc)
+    validate_inputs(normcc, marker_idx_sorted, rp, perc, check_values=False)
     if group is not None:
         from .sharded import crwr_impute_sharded
         return crwr_impute_sharded(normcc, marker_idx_sorted, rp, perc, tol, max_steps, dtype, device, return_info, group)

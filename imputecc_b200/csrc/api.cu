@@ -50,6 +50,7 @@ struct Layout {
     size_t fb_rows, xbuf, cand, merged, counts, counts_scan, total;
     size_t d_acc, d_oldv, d_ord, d_tbits, d_kbits;
     size_t k1_row_cnt, k1_col_cnt, k1_col_ptr, k1_col_fill, k1_csc_row, k1_csc_val, k1_scale, k1_iso, k1_row_val;
+    size_t k1_bad;
     size_t bytes;
     long long cand_cap;
     long long dense_warps;
@@ -116,6 +117,7 @@ bool make_layout(const crwr_config& c, Layout& L) {
     L.k1_scale = bump(off, 8 * (size_t)n);
     L.k1_iso = bump(off, 4 * (size_t)n);
     L.k1_row_val = bump(off, 8 * (size_t)pcap);
+    L.k1_bad = bump(off, 8);
     L.bytes = (off + 255) & ~(size_t)255;
     return true;
 }
@@ -513,6 +515,8 @@ int32_t crwr_build_transition(crwr_handle h, const int64_t* d_indptr, const int3
     sc.isolated = h->at<int32_t>(L.k1_iso);
     sc.row_val = h->at<double>(L.k1_row_val);
     sc.total = h->at<long long>(L.total);
+    sc.bad = h->at<int32_t>(L.k1_bad);
+    CUDA_TRY(cudaMemsetAsync(sc.bad, 0, 8, st));
     CUDA_TRY(cudaMemsetAsync(sc.col_cnt, 0, 4 * (size_t)(n + 1), st));
     CUDA_TRY(cudaMemsetAsync(sc.col_fill, 0, 4 * (size_t)n, st));
     CUDA_TRY(cudaMemsetAsync(sc.row_cnt, 0, 4 * (size_t)(n + 1), st));
@@ -539,8 +543,11 @@ int32_t crwr_build_transition(crwr_handle h, const int64_t* d_indptr, const int3
                                                                 h->at<float>(L.p_vals));
     LAUNCH_CHECK();
     long long total = 0;
+    int bad = 0;
     CUDA_TRY(cudaMemcpyAsync(&total, sc.total, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&bad, sc.bad, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (bad) CRWR_FAIL(CRWR_ERR_INVALID, "contact values must be finite and non-negative");
     h->p_nnz = total;
     h->have_p = true;
     if (h_nnz_out) *h_nnz_out = total;

@@ -15,19 +15,27 @@
 
 namespace crwr {
 
-// Exclusive scan of int32 counts into OutT offsets (n+1 entries) by ONE CTA of 1024 threads.
+// Exclusive scan of int32 counts into OutT offsets (n+1 entries) by ONE CTA of 1024 threads, 8 items per
+// thread and iteration (n is at most a few hundred thousand: one CTA keeps it a single short launch).
 template <typename OutT>
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __restrict__ cnt, OutT* __restrict__ out,
                                                               long long n, long long* total_out) {
+    constexpr int ITEMS = 8;
     __shared__ long long warp_tot[32];
     __shared__ long long carry_s;
     const int t = threadIdx.x;
     if (t == 0) carry_s = 0;
     __syncthreads();
-    for (long long base = 0; base < n; base += 1024) {
-        const long long i = base + t;
-        const long long v = (i < n) ? (long long)cnt[i] : 0;
-        long long incl = v;
+    for (long long base = 0; base < n; base += 1024 * ITEMS) {
+        const long long i0 = base + (long long)t * ITEMS;
+        long long v[ITEMS];
+        long long mine = 0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            v[k] = (i0 + k < n) ? (long long)cnt[i0 + k] : 0;
+            mine += v[k];
+        }
+        long long incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             long long w = __shfl_up_sync(kFull, incl, o);
@@ -46,11 +54,14 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
             warp_tot[t] = wi - w;
         }
         __syncthreads();
-        const long long carry = carry_s;
-        const long long excl = carry + warp_tot[t >> 5] + incl - v;
-        if (i < n) out[i] = (OutT)excl;
+        long long run = carry_s + warp_tot[t >> 5] + incl - mine;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            if (i0 + k < n) out[i0 + k] = (OutT)run;
+            run += v[k];
+        }
         __syncthreads();
-        if (t == 1023) carry_s = excl + v;
+        if (t == 1023) carry_s = run;
         __syncthreads();
     }
     if (t == 0) {
@@ -70,6 +81,7 @@ struct TransitionScratch {
     int32_t* isolated;    // [N]
     double* row_val;      // [nnz + N] unscaled float64 values of B in CSR order
     long long* total;     // [1]
+    int32_t* bad;         // [1] set when a contact value is negative, NaN or infinite
 };
 
 __global__ void transition_count_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
@@ -80,7 +92,9 @@ __global__ void transition_count_kernel(const int64_t* __restrict__ indptr, cons
     int cnt = 0;
     for (long long e = indptr[r]; e < indptr[r + 1]; ++e) {
         const int c = indices[e];
-        if (c != r && data[e] != 0.0) {
+        const double v = data[e];
+        if (!(v >= 0.0) || v > 1.7976931348623157e308) *sc.bad = 1;      // negative, NaN or +inf
+        if (c != r && v != 0.0) {
             ++cnt;
             atomicAdd(&sc.col_cnt[new_of_old[c]], 1);
         }

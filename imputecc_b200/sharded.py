@@ -170,7 +170,7 @@ def crwr_impute_sharded(normcc, marker_idx_sorted, rp, perc, tol=DEFAULT_TOL, ma
     Every rank passes the same inputs and receives the same imputed matrix."""
     torch = _torch()
     import torch.distributed as dist
-    validate_inputs(normcc, marker_idx_sorted, rp, perc)
+    validate_inputs(normcc, marker_idx_sorted, rp, perc, check_values=False)
     if group is None:
         group = dist.group.WORLD
     world = dist.get_world_size(group)

@@ -256,3 +256,12 @@ def test_capacity_regrow(cuda_device):
         assert _bit_equal(w.result().tocsc(), load_csr(rec, "walk32"))
     finally:
         w.close()
+
+
+def test_bad_contact_values_are_rejected_on_the_device(cuda_device):
+    M = synth.contact_matrix(300, 30, 8, 1, seed=9)
+    for bad in (-1.0, np.nan, np.inf):
+        B = M.copy()
+        B.data[7] = bad
+        with pytest.raises(ValueError, match="finite and non-negative"):
+            pkg.crwr_impute(B, np.array([3, 9, 40]), 0.5, 80, device=cuda_device)
