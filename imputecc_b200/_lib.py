@@ -57,6 +57,7 @@ _SIGNATURES = {
     "crwr_set_row_hints": (C.c_int32, [_P, C.c_int64, C.c_int64]),
     "crwr_get_shape": (C.c_int32, [_P, C.POINTER(C.c_int64)]),
     "crwr_profile": (C.c_int32, [_P, C.c_int32]),
+    "crwr_profile_phases": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "crwr_profile_read": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _P]),
     "crwr_walk_enqueue": (C.c_int32, [_P, C.c_int32, _P]),
     "crwr_step_propagate": (C.c_int32, [_P, _P]),

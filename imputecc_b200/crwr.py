@@ -28,6 +28,8 @@ from ._lib import CRWR_F32, CRWR_F64, CapacityError, Config, Status, StepRecord
 
 DEFAULT_TOL = 0.01          # imputation.py:120
 DEFAULT_MAX_STEPS = 500     # utility.py:281
+# walk steps enqueued between two status polls (steps after the stop rule fired are skipped on the device)
+POLL_EVERY = int(__import__("os").environ.get("CRWR_POLL_EVERY", "4"))
 
 
 def _torch():
@@ -329,7 +331,7 @@ class Walker:
         hints = next_row_hints(0, 0, perc, 0)
         while True:
             # steps 0 and 1 change the row shapes most: poll after each; later run four at a time
-            chunk = 1 if issued < 2 else 4
+            chunk = 1 if issued < 2 else POLL_EVERY
             chunk = min(chunk, max_steps - issued)
             self.set_row_hints(*hints)
             _lib.check(lib.crwr_walk_enqueue(h, chunk, self._stream()))

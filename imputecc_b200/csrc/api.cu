@@ -142,6 +142,9 @@ struct crwr_handle_s {
     long long hint_len_eff = 128;               // expected longest product row
     bool profile = false;                       // CUDA events around every main propagate launch
     std::vector<cudaEvent_t> ev;                // start/end pairs
+    std::vector<cudaEvent_t> marks;             // profile mode: step start + one event after each kernel of the step
+    std::vector<int> mark_ids;
+    double phase_ms[4] = {0, 0, 0, 0};
     template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
 };
 
@@ -339,6 +342,15 @@ int launch_finish(crwr_handle_s* h, int do_select, const void* gathered, cudaStr
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+void prof_mark(crwr_handle_s* h, cudaStream_t st, int id) {
+    if (!h->profile) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    h->marks.push_back(e);
+    h->mark_ids.push_back(id);
+}
+
 template <typename T>
 int enqueue_step(crwr_handle_s* h, cudaStream_t st) {
     // the step index and buffer parity are deterministic on the host: every enqueued step either
@@ -352,9 +364,13 @@ int enqueue_step(crwr_handle_s* h, cudaStream_t st) {
     } else {
         // propagate (+ level-0/1 histograms in its epilogue) -> large-row kernel (+ scans in its last CTA)
         // -> level-1 histogram pass (skipped on the device when the prediction held) -> gather (+ finish)
+        prof_mark(h, st, 0);
         if (launch_propagate<T>(h, parity, true, st)) return -1;
+        prof_mark(h, st, 1);
         if (launch_hist<T>(h, parity ^ 1, 1, 1, st)) return -1;
+        prof_mark(h, st, 2);
         if (launch_gather<T>(h, parity ^ 1, 1, st)) return -1;
+        prof_mark(h, st, 3);
     }
     h->steps_enqueued = step + 1;
     return 0;
@@ -634,6 +650,24 @@ int32_t crwr_profile_read(crwr_handle h, double* h_total_ms, int64_t* h_launches
     h->ev.clear();
     *h_total_ms = total;
     *h_launches = n;
+    // step phases: [1] propagate + large-row kernel (+ scans), [2] level-1 histogram pass, [3] gather + finish
+    double phase[4] = {0, 0, 0, 0};
+    for (size_t i = 1; i < h->marks.size(); ++i) {
+        float ms = 0.f;
+        const int id = h->mark_ids[i];
+        if (id > 0 && h->mark_ids[i - 1] == id - 1 && cudaEventElapsedTime(&ms, h->marks[i - 1], h->marks[i]) == cudaSuccess)
+            phase[id] += ms;
+    }
+    for (cudaEvent_t e : h->marks) cudaEventDestroy(e);
+    h->marks.clear();
+    h->mark_ids.clear();
+    h->phase_ms[1] = phase[1]; h->phase_ms[2] = phase[2]; h->phase_ms[3] = phase[3];
+    return CRWR_OK;
+}
+
+int32_t crwr_profile_phases(crwr_handle h, double* h_ms3) {
+    if (!h || !h_ms3) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    h_ms3[0] = h->phase_ms[1]; h_ms3[1] = h->phase_ms[2]; h_ms3[2] = h->phase_ms[3];
     return CRWR_OK;
 }
 

@@ -709,7 +709,12 @@ template <typename T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T> a, DenseScratch<T> sc) {
     __shared__ unsigned int win[kHistWin];
     if (a.st->done) return;
-    if (a.st->fb_count == 0 && !a.fused_select) return;
+    if (a.st->fb_count == 0) {
+        // the usual case: no row was deferred, the step's histogram is already complete.  No CTA has row
+        // work, so no "last CTA" is needed: CTA 0 scans, the others leave at once.
+        if (a.fused_select && blockIdx.x == 0) scan_tail<T, WARPS * 32>(a.st, a.hist);
+        return;
+    }
     for (int i = threadIdx.x; i < kHistWin; i += WARPS * 32) win[i] = 0u;
     __syncthreads();
     const unsigned n_fb = a.st->fb_count;

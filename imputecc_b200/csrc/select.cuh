@@ -36,9 +36,10 @@ __device__ __noinline__ void scan_level(WalkState* st, const unsigned long long*
     __shared__ unsigned long long s_total;
     const unsigned long long* h = hist + (size_t)level * kSelectBins;
     const int t = threadIdx.x;
+    unsigned long long c[BPT];
     unsigned long long mine = 0;
-#pragma unroll 8
-    for (int i = 0; i < BPT; ++i) mine += __ldcg(h + t * BPT + i);
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) { c[i] = __ldcg(h + t * BPT + i); mine += c[i]; }
     unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -88,15 +89,14 @@ __device__ __noinline__ void scan_level(WalkState* st, const unsigned long long*
     __syncthreads();                                            // all reads precede the single write
     if (target >= excl && target < excl + mine) {          // exactly one thread: the bin lies in its range
         unsigned long long run = excl;
+#pragma unroll
         for (int i = 0; i < BPT; ++i) {
-            const unsigned long long c = __ldcg(h + t * BPT + i);
-            if (target < run + c) {
+            if (target >= run && target < run + c[i]) {
                 st->below = below0 + run;
                 st->prefix = (prefix0 << kSelectBits) | (unsigned long long)(t * BPT + i);
-                st->bin_count = c;
-                break;
+                st->bin_count = c[i];
             }
-            run += c;
+            run += c[i];
         }
     }
     __syncthreads();
@@ -169,9 +169,17 @@ __device__ void finish_step_body(const FinishArgs& a) {
     __shared__ unsigned long long wbest[32];
     __shared__ unsigned long long s_xk, s_xk1, s_total, s_succ;
     __shared__ int s_have1, s_ovf;
-    WalkState* st = a.st;
+    // the walk state is worked on in shared memory (one coalesced read, one coalesced write) instead of
+    // through dozens of dependent L2 round trips by thread 0; no other CTA touches it at this point
+    __shared__ WalkState s_state;
+    WalkState* const gst = a.st;
     const int t = threadIdx.x;
-
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(gst);
+        unsigned* dst = reinterpret_cast<unsigned*>(&s_state);
+        for (int i = t; i < (int)(sizeof(WalkState) / 4); i += blockDim.x) dst[i] = __ldcg(src + i);
+    }
+    WalkState* st = &s_state;
     if (t == 0) { s_have1 = 0; s_xk = 0; s_xk1 = 0; s_ovf = 0; }
     __syncthreads();
 
@@ -335,7 +343,12 @@ __device__ void finish_step_body(const FinishArgs& a) {
         a.own_block[0] = 0;
         a.own_block[1] = ~0ull;
     }
-    __syncthreads();   // thread 0 has consumed the exchanged counters
+    __syncthreads();   // thread 0 has consumed the exchanged counters and updated the state
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(&s_state);
+        unsigned* dst = reinterpret_cast<unsigned*>(gst);
+        for (int i = t; i < (int)(sizeof(WalkState) / 4); i += blockDim.x) dst[i] = src[i];
+    }
     for (int i = t; i < kSelectLevels * kSelectBins + kXExtras; i += blockDim.x) a.hist[i] = 0ull;
 }
 
@@ -353,15 +366,21 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const T* __restrict__ 
     const long long n = (long long)st->cursor;
     const K prefix = (K)st->prefix;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const T v = vals[i];
-        if (v == (T)0) continue;                      // zero padding of a row reservation
-        const K key = KO::enc(v);
-        if (level == 0) {
-            atomicAdd(&sh[(unsigned)(key >> (KO::bits - kSelectBits))], 1u);
-        } else {
-            if ((key >> (KO::bits - kSelectBits)) == prefix)
-                atomicAdd(&sh[(unsigned)(key >> (KO::bits - 2 * kSelectBits)) & (kSelectBins - 1)], 1u);
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        T vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const long long i = i0 + u * stride; vv[u] = i < n ? vals[i] : (T)0; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const T v = vv[u];
+            if (v == (T)0) continue;                  // zero padding of a row reservation (or past the end)
+            const K key = KO::enc(v);
+            if (level == 0) {
+                atomicAdd(&sh[(unsigned)(key >> (KO::bits - kSelectBits))], 1u);
+            } else {
+                if ((key >> (KO::bits - kSelectBits)) == prefix)
+                    atomicAdd(&sh[(unsigned)(key >> (KO::bits - 2 * kSelectBits)) & (kSelectBins - 1)], 1u);
+            }
         }
     }
     __syncthreads();
@@ -394,17 +413,23 @@ __global__ void __launch_bounds__(512) select_gather_kernel(const T* __restrict_
     const long long stride = (long long)gridDim.x * blockDim.x;
     K best = ~(K)0;
     bool have = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const T v = vals[i];
-        if (v == (T)0) continue;                      // zero padding of a row reservation
-        const K key = KO::enc(v);
-        const K p = key >> (KO::bits - 2 * kSelectBits);
-        if (p == prefix) {
-            unsigned long long idx = atomicAdd(&block[0], 1ull);
-            if (idx < cand_cap) block[kCandHeader + idx] = (unsigned long long)key;
-        } else if (p > prefix) {
-            if (!have || key < best) best = key;
-            have = true;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        T vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const long long i = i0 + u * stride; vv[u] = i < n ? vals[i] : (T)0; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const T v = vv[u];
+            if (v == (T)0) continue;                  // zero padding of a row reservation (or past the end)
+            const K key = KO::enc(v);
+            const K p = key >> (KO::bits - 2 * kSelectBits);
+            if (p == prefix) {
+                unsigned long long idx = atomicAdd(&block[0], 1ull);
+                if (idx < cand_cap) block[kCandHeader + idx] = (unsigned long long)key;
+            } else if (p > prefix) {
+                if (!have || key < best) best = key;
+                have = true;
+            }
         }
     }
     unsigned long long b64 = have ? (unsigned long long)best : ~0ull;

@@ -177,6 +177,9 @@ int32_t crwr_symmetrise_write(int32_t dtype, int64_t m, const int64_t* d_indptr,
  * the launches since the last read (launches skipped after the stop rule count as ~0) and clears. */
 int32_t crwr_profile(crwr_handle h, int32_t enable);
 int32_t crwr_profile_read(crwr_handle h, double* h_total_ms, int64_t* h_launches, void* stream);
+/* After crwr_profile_read: summed durations (ms) of the step phases since the previous read:
+ * [0] propagate + large-row kernel, [1] level-1 histogram pass, [2] candidate gather + finish. */
+int32_t crwr_profile_phases(crwr_handle h, double* h_ms3);
 
 /* Launch counter: kernels this library launched since the last reset (bench gpu_launches). */
 int64_t crwr_launch_count(int32_t reset);

@@ -35,7 +35,9 @@ for rep in range(args.reps):
     wall = time.perf_counter() - t0
     tot, nl = _lib.C.c_double(0), _lib.C.c_int64(0)
     lib.crwr_profile_read(w.handle, _lib.C.byref(tot), _lib.C.byref(nl), w._stream())
-    print("rep %d: %d steps, wall %.3f ms, propagate total %.3f ms over %d launches" % (rep, st.steps_done, wall * 1e3, tot.value, nl.value))
+    ph = (_lib.C.c_double * 3)()
+    lib.crwr_profile_phases(w.handle, ph)
+    print("rep %d: %d steps, wall %.3f ms, propagate total %.3f ms over %d launches | phases: prop+dense %.3f hist1 %.3f gather+finish %.3f" % (rep, st.steps_done, wall * 1e3, tot.value, nl.value, ph[0], ph[1], ph[2]))
 shape = (_lib.C.c_int64 * 8)()
 lib.crwr_get_shape(w.handle, shape)
 print("shape H %d limit %d kmax %d scap %d warps %d per_warp %d grid %d sms %d" % tuple(shape))
