@@ -109,6 +109,17 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload, dtype):
+    """dram__bytes_read.sum + dram__bytes_write.sum per propagate_kernel launch from the committed
+    `ncu --set full` capture of this command (profiles/traffic.json), or None when not captured."""
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as fh:
+            rec = json.load(fh).get("%s_%s" % (workload, dtype))
+            return (rec["bytes_per_launch"], rec["source"]) if rec else (None, None)
+    except Exception:
+        return (None, None)
+
+
 def pinned_csr(M):
     """scipy CSR whose arrays live in pinned host memory (asynchronous H2D)."""
     import scipy.sparse as sp
@@ -251,6 +262,8 @@ def main():
     one_walk()
     tot_ms, n_launch = _lib.C.c_double(0), _lib.C.c_int64(0)
     _lib.check(lib.crwr_profile_read(walker.handle, _lib.C.byref(tot_ms), _lib.C.byref(n_launch), walker._stream()))
+    phases = (_lib.C.c_double * 3)()
+    lib.crwr_profile_phases(walker.handle, phases)
     lib.crwr_profile(walker.handle, 0)
     steps_per_walk = len(trace)
     prop_ms_per_launch = tot_ms.value / max(steps_per_walk, 1)       # launches after the stop are no-ops (~0 ms)
@@ -293,6 +306,7 @@ def main():
     step_ms = walk_ms / max(walk_steps, 1)
     step_gbs = (total_bytes / max(steps_per_walk, 1)) / (step_ms * 1e-3) / 1e9
     h2d = M.indptr.size * 8 + M.indices.size * 4 + M.data.size * 8 + n * 4
+    traffic, traffic_src = measured_traffic(args.workload, args.dtype) if world == 1 else (None, None)
 
     line = {
         "metric": "crwr_walk_steps_per_s", "value": value,
@@ -303,11 +317,15 @@ def main():
         "walk_steps_per_imputation": steps_per_walk, "us_per_walk_step": 1e3 * step_ms,
         "imputation_wall_ms_e2e": e2e_ms / args.steps,
         "roofline": {"bound": "hbm", "kernel": "propagate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "bytes_per_launch": prop_bytes_launch, "us_per_launch": 1e3 * prop_ms_per_launch,
                      "whole_step": {"bytes": total_bytes / max(steps_per_walk, 1), "us": 1e3 * step_ms,
                                     "achieved": step_gbs, "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0}},
         "e2e": {"value": e2e_value, "unit": "walk-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "step_phases_us": {"propagate+large_rows+scan": 1e3 * phases[0] / max(steps_per_walk - 1, 1),
+                           "level1_histogram": 1e3 * phases[1] / max(steps_per_walk - 1, 1),
+                           "gather+finish": 1e3 * phases[2] / max(steps_per_walk - 1, 1),
+                           "note": "CUDA-event durations inside one profiled walk (unsharded walks only)"},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
     }
