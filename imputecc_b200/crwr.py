@@ -29,7 +29,9 @@ from ._lib import CRWR_F32, CRWR_F64, CapacityError, Config, Status, StepRecord
 DEFAULT_TOL = 0.01          # imputation.py:120
 DEFAULT_MAX_STEPS = 500     # utility.py:281
 # walk steps enqueued between two status polls (steps after the stop rule fired are skipped on the device)
-POLL_EVERY = int(__import__("os").environ.get("CRWR_POLL_EVERY", "4"))
+POLL_EVERY = int(__import__("os").environ.get("CRWR_POLL_EVERY", "16"))
+_m = __import__("os").environ.get("CRWR_WALK_MODE")
+WALK_MODE = int(_m) if _m is not None else None     # developer override of crwr_set_mode
 
 
 def _torch():
@@ -126,6 +128,19 @@ def shard_rows(n_rows: int, n_shards: int, weights: Optional[np.ndarray] = None)
 
 def default_iterate_cap(n_rows: int, n_contigs: int) -> int:
     return int(min(n_rows * n_contigs, max(1 << 22, 2048 * n_rows)))
+
+
+def poll_chunk(issued: int) -> int:
+    """Walk steps to enqueue before the next status poll.
+
+    Steps 0 and 1 change the row shapes most, so the kernel sizing hints are refreshed after each;
+    after step 3 the kept share has been observed and the walk runs in long chunks (steps enqueued
+    after the stop rule fired are skipped on the device)."""
+    if issued < 2:
+        return 1
+    if issued < 4:
+        return 2
+    return POLL_EVERY
 
 
 def next_row_hints(max_row_len: int, max_kept: int, perc: float, issued: int):
@@ -303,8 +318,14 @@ class Walker:
             torch.cuda.current_stream(self.device).synchronize()
 
     # -- the walk -----------------------------------------------------------------------------
+    def set_mode(self, mode: int):
+        """1: persistent cooperative kernel per chunk of steps (default); 0: one launch per phase."""
+        _lib.check(self.lib.crwr_set_mode(self.handle, int(mode)))
+
     def walk_init(self, rp, perc, tol=DEFAULT_TOL, max_steps=DEFAULT_MAX_STEPS):
         self._walk_args = (float(rp), float(perc), float(tol), int(max_steps))
+        if WALK_MODE is not None:
+            self.set_mode(WALK_MODE)
         _lib.check(self.lib.crwr_walk_init(self.handle, float(rp), float(perc), float(tol), int(max_steps), self._stream()))
 
     def poll(self) -> Status:
@@ -331,7 +352,7 @@ class Walker:
         hints = next_row_hints(0, 0, perc, 0)
         while True:
             # steps 0 and 1 change the row shapes most: poll after each; later run four at a time
-            chunk = 1 if issued < 2 else POLL_EVERY
+            chunk = poll_chunk(issued)
             chunk = min(chunk, max_steps - issued)
             self.set_row_hints(*hints)
             _lib.check(lib.crwr_walk_enqueue(h, chunk, self._stream()))

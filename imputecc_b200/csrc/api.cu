@@ -13,6 +13,7 @@
 #include "propagate.cuh"
 #include "transition.cuh"
 #include "finish.cuh"
+#include "walk.cuh"
 
 using namespace crwr;
 
@@ -135,6 +136,11 @@ struct crwr_handle_s {
     int steps_enqueued;
     PropShape shape;                // run-time sizing of the main propagate kernel
     int grid;                       // its persistent grid size
+    int mode = 1;                   // 1: one cooperative kernel per chunk of steps; 0: one launch per phase
+    int mode_next = 1;              // takes effect at the next crwr_walk_init
+    bool coop_ok = false;           // device supports cooperative launches
+    int coop_grid = 0;              // co-resident CTAs of walk_chunk_kernel for the current shape
+    size_t coop_smem = 0;
     int max_smem_optin;
     double rp, perc;
     WalkState* h_state = nullptr;               // pinned host mirror of the device state (polls)
@@ -201,6 +207,7 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
     int w = (int)((57344 - kHistWin * sizeof(unsigned int)) / sh.per_warp);
     if (w < 1) w = 1;
     if (w > 8) w = 8;
+    while (w & (w - 1)) --w;        // power of two: block-wide scans are templated on the CTA size
     sh.warps = w;
     const size_t smem = sh.per_warp * (size_t)w + kHistWin * sizeof(unsigned int);
     cudaError_t e = cudaFuncSetAttribute(propagate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -211,6 +218,24 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
     if (per_sm < 1) per_sm = 1;
     h->shape = sh;
     h->grid = per_sm * h->sm_count;
+    // the persistent walk kernel shares the per-warp layout; its CTA also hosts the 4096-bin histogram of the
+    // level-1 pass and the finish step's scratch in the same dynamic shared memory
+    h->coop_grid = 0;
+    if (h->coop_ok) {
+        size_t cs = smem;
+        if (cs < (size_t)kSelectBins * sizeof(unsigned int)) cs = (size_t)kSelectBins * sizeof(unsigned int);
+        if (cs < kFinishScratchBytes) cs = kFinishScratchBytes;
+        cs = (cs + 255) & ~(size_t)255;
+        if (cs <= (size_t)h->max_smem_optin &&
+            cudaFuncSetAttribute(walk_chunk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs) == cudaSuccess) {
+            int cper = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cper, walk_chunk_kernel<T>, w * 32, cs) == cudaSuccess && cper >= 1) {
+                h->coop_grid = cper * h->sm_count;
+                h->coop_smem = cs;
+            }
+        }
+        (void)cudaGetLastError();
+    }
     return 0;
 }
 
@@ -340,6 +365,60 @@ int launch_finish(crwr_handle_s* h, int do_select, const void* gathered, cudaStr
     finish_step_kernel<T><<<1, 1024, 0, st>>>(finish_args(h, do_select, gathered));
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <typename T>
+DenseScratch<T> dense_scratch(crwr_handle_s* h) {
+    const Layout& L = h->L;
+    DenseScratch<T> sc;
+    sc.acc = h->at<T>(L.d_acc);
+    sc.oldv = h->at<T>(L.d_oldv);
+    sc.ord = h->at<int32_t>(L.d_ord);
+    sc.tbits = h->at<uint32_t>(L.d_tbits);
+    sc.kbits = h->at<uint32_t>(L.d_kbits);
+    sc.n = h->cfg.n_contigs;
+    sc.words = L.words;
+    return sc;
+}
+
+FinishArgs finish_args(crwr_handle_s* h, int do_select, const void* gathered);
+
+// One cooperative launch that runs up to n_steps walk steps (walk.cuh).
+template <typename T>
+int launch_walk_chunk(crwr_handle_s* h, int n_steps, cudaStream_t st) {
+    const Layout& L = h->L;
+    WalkChunkArgs<T> w;
+    w.prop = prop_args<T>(h, 0, true);
+    for (int b = 0; b < 2; ++b)
+        w.buf[b] = IterBuf<T>{h->at<int32_t>(L.it_cols[b]), h->at<T>(L.it_vals[b]), h->at<long long>(L.it_ptr[b]),
+                              h->at<int32_t>(L.it_len[b])};
+    w.shape = h->shape;
+    w.dense = dense_scratch<T>(h);
+    w.dense_warps = L.dense_warps;
+    w.fin = finish_args(h, 1, nullptr);
+    w.hist = hist_ptr(h);
+    w.cand_block = h->at<unsigned long long>(L.cand);
+    w.cand_cap = (unsigned long long)L.cand_cap;
+    w.n_steps = n_steps;
+    const int rows = w.prop.n_rows;
+    int grid = (rows + h->shape.warps - 1) / h->shape.warps;
+    if (grid > h->coop_grid) grid = h->coop_grid;
+    if (grid < 1) grid = 1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profile) {
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
+        cudaEventRecord(e0, st);
+    }
+    void* args[] = {(void*)&w};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)walk_chunk_kernel<T>, dim3(grid), dim3(h->shape.warps * 32), args,
+                                                h->coop_smem, st);
+    ++g_launches;
+    if (h->profile) {
+        cudaEventRecord(e1, st);
+        h->ev.push_back(e0);
+        h->ev.push_back(e1);
+    }
+    return e == cudaSuccess ? 0 : -1;
 }
 
 void prof_mark(crwr_handle_s* h, cudaStream_t st, int id) {
@@ -481,6 +560,10 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     h->walking = false;
     h->steps_enqueued = 0;
     h->max_smem_optin = smem_optin;
+    {
+        int coop = 0;
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device) == cudaSuccess) h->coop_ok = coop != 0;
+    }
     h->h_state = acquire_pinned_state();
     if (!h->h_state) {
         delete h;
@@ -627,6 +710,7 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     h->perc = perc;
     h->steps_enqueued = 0;
     h->walking = true;
+    h->mode = h->mode_next;
     return CRWR_OK;
 }
 
@@ -684,6 +768,21 @@ int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept)
     return CRWR_OK;
 }
 
+int32_t crwr_set_mode(crwr_handle h, int32_t mode) {
+    if (!h || (mode != 0 && mode != 1)) CRWR_FAIL(CRWR_ERR_INVALID, "mode must be 0 or 1");
+    h->mode_next = mode;            // applied by the next crwr_walk_init: a walk never changes mode midway
+    return CRWR_OK;
+}
+
+int32_t crwr_phase_ns(crwr_handle h, uint64_t* h_out8, void* stream) {
+    if (!h || !h_out8) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(h->h_state, h->ws + h->L.state, sizeof(WalkState), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < 8; ++i) h_out8[i] = h->h_state->phase_ns[i];
+    return CRWR_OK;
+}
+
 int32_t crwr_get_shape(crwr_handle h, int64_t* h_out8) {
     if (!h || !h_out8) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
     h_out8[0] = h->shape.H; h_out8[1] = h->shape.limit; h_out8[2] = h->shape.kmax; h_out8[3] = h->shape.scap;
@@ -697,6 +796,14 @@ int32_t crwr_walk_enqueue(crwr_handle h, int32_t n_steps, void* stream) {
         CRWR_FAIL(CRWR_ERR_STATE, "crwr_walk_enqueue is for unsharded walks; use the crwr_step_* calls");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    // the persistent kernel pays off when a step's phases are short (small rows: several warps per CTA); with
+    // one-warp CTAs (long rows) the separate launches are faster, and the choice can change between chunks
+    if (h->mode == 1 && h->coop_grid > 0 && h->shape.warps >= 2 && n_steps > 0) {
+        int e = h->cfg.dtype == CRWR_F64 ? launch_walk_chunk<double>(h, n_steps, st) : launch_walk_chunk<float>(h, n_steps, st);
+        if (e) CRWR_FAIL(CRWR_ERR_CUDA, "cooperative walk launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        h->steps_enqueued += n_steps;
+        return CRWR_OK;
+    }
     for (int i = 0; i < n_steps; ++i) {
         int e = h->cfg.dtype == CRWR_F64 ? enqueue_step<double>(h, st) : enqueue_step<float>(h, st);
         if (e) CRWR_FAIL(CRWR_ERR_CUDA, "step launch failed: %s", cudaGetErrorString(cudaGetLastError()));

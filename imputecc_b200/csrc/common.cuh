@@ -111,6 +111,7 @@ struct WalkState {
     int32_t hist1_ready;               // level-1 histogram already holds the counts of the selected level-0 bin
     unsigned int tick_dense, tick_hist1, tick_gather;   // last-CTA tickets
     unsigned int tick_prop;
+    unsigned long long phase_ns[8];    // persistent kernel: summed nanoseconds per phase (CTA 0's view), diagnostics
     int32_t scan_done;                 // the level scans of this step already ran (in the propagate kernel's last CTA)
     int32_t pad3;
 };

@@ -215,50 +215,6 @@ __device__ __forceinline__ uint32_t hash_col(int32_t j, int log_h) {
     return ((uint32_t)j * 0x9E3779B1u) >> (32 - log_h);
 }
 
-// Output space for a row is reserved as soon as its candidate count is known (lane 0 issues the atomic;
-// the result is only broadcast when the row is written, so the round trip overlaps the epilogue).
-__device__ __forceinline__ long long reserve_row(WalkState* st, int n_cand) {
-    long long base = 0;
-    if (lane_id() == 0) base = (long long)atomicAdd(&st->cursor, (unsigned long long)n_cand);
-    return base;      // valid in lane 0 only
-}
-
-// Writes one finished row into its reserved space.  `emit(i, &col, &val)` yields the i-th candidate
-// (i < n_cand) in output order; zero values are dropped (csr_matmat / csr_plus_csr never store them) and
-// the unused tail of the reservation is padded with zeros, which every later pass over the value array
-// ignores (a stored value is never zero).
-template <typename T, typename Emit>
-__device__ __forceinline__ void write_row(const PropArgs<T>& a, int row, long long base_lane0, int n_cand, int n_nonzero,
-                                          Emit emit) {
-    const int lane = lane_id();
-    const long long base = __shfl_sync(kFull, base_lane0, 0);
-    const bool fits = base + n_cand <= a.out_cap;
-    if (lane == 0) {
-        a.out.row_ptr[row] = fits ? base : 0;
-        a.out.row_len[row] = fits ? n_nonzero : 0;
-        if (!fits) a.st->capacity_overflow = 1;
-        atomicMax(&a.st->max_row_len, n_nonzero);
-        atomicAdd(&a.st->nnz_exact, (unsigned long long)n_nonzero);
-    }
-    if (!fits) return;
-    int written = 0;
-    for (int b = 0; b < n_cand; b += 32) {
-        int i = b + lane;
-        int32_t c = 0;
-        T v = (T)0;
-        if (i < n_cand) emit(i, c, v);
-        bool nz = (i < n_cand) && (v != (T)0);
-        unsigned m = __ballot_sync(kFull, nz);
-        if (nz) {
-            long long o = base + written + __popc(m & lanemask_lt());
-            a.out.cols[o] = c;
-            a.out.vals[o] = v;
-        }
-        written += __popc(m);
-    }
-    for (int i = written + lane; i < n_cand; i += 32) { a.out.cols[base + i] = -1; a.out.vals[base + i] = (T)0; }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Main kernel: shared-memory hash accumulator, sized at run time.
 //
@@ -363,10 +319,10 @@ __device__ __forceinline__ void warp_sort_kept_regs(int32_t* kcol, T* kval, T* s
     __syncwarp();
 }
 
+// One walk step's propagation for the rows of this shard (all CTAs of the grid cooperate through the
+// row counter).  Called by every thread of every CTA; smem_raw is the CTA's dynamic shared memory.
 template <typename T>
-__global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape sh) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (a.st->done) return;
+__device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropShape& sh, unsigned char* smem_raw) {
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const int H = sh.H, KMAX = sh.kmax, SCAP = sh.scap, LIMIT = sh.limit;
@@ -390,10 +346,10 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
     for (int i = lane; i < HT; i += 32) tkey[i] = -1;
     __syncthreads();
 
-    const bool cut_on = a.st->cut_on != 0;
-    const T cut = (T)a.st->cut;
-    const bool pred_valid = a.st->pred_valid != 0;
-    const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)a.st->pred_prefix0;
+    const bool cut_on = __ldcg(&a.st->cut_on) != 0;
+    const T cut = (T)__ldcg(&a.st->cut);
+    const bool pred_valid = __ldcg(&a.st->pred_valid) != 0;
+    const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)__ldcg(&a.st->pred_prefix0);
     const int32_t* __restrict__ pcols = a.p_cols;
     const T* __restrict__ pvals = a.p_vals;
 
@@ -458,8 +414,8 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
         // ---- read the row, dropping entries at or below the previous cut (strict >, utility.py:290)
         const long long ptr = a.in.row_ptr[row];
         const int len = a.in.row_len[row];
-        const int32_t* __restrict__ rc = a.in.cols + ptr;
-        const T* __restrict__ rv = a.in.vals + ptr;
+        const int32_t* rc = a.in.cols + ptr;      // plain (coherent) loads: the persistent walk kernel rewrites
+        const T* rv = a.in.vals + ptr;            // this buffer two steps later
         int nk = 0;
         for (int b = 0; b < len; b += 128) {
             int32_t c[4];
@@ -664,6 +620,13 @@ __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape
     if (a.hist) hist_window_flush<T>(a.hist, win);
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape sh) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.st->done) return;
+    propagate_rows<T>(a, sh, smem_raw);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Large-row kernel: same algorithm with a dense accumulator of N entries per warp in global
 // memory (L2 resident), for rows whose kept list or output does not fit the hash variant.
@@ -705,30 +668,21 @@ __device__ __forceinline__ void dense_accumulate_row_of_p(const PropArgs<T>& a, 
     }
 }
 
-template <typename T, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T> a, DenseScratch<T> sc) {
-    __shared__ unsigned int win[kHistWin];
-    if (a.st->done) return;
-    if (a.st->fb_count == 0) {
-        // the usual case: no row was deferred, the step's histogram is already complete.  No CTA has row
-        // work, so no "last CTA" is needed: CTA 0 scans, the others leave at once.
-        if (a.fused_select && blockIdx.x == 0) scan_tail<T, WARPS * 32>(a.st, a.hist);
-        return;
-    }
-    for (int i = threadIdx.x; i < kHistWin; i += WARPS * 32) win[i] = 0u;
-    __syncthreads();
-    const unsigned n_fb = a.st->fb_count;
+// Rows deferred by the main kernel, one per warp at a time; gw = this warp's slot in the dense scratch.
+// Ends with the warp's totals published; the caller flushes the histogram window after a CTA barrier.
+template <typename T>
+__device__ __noinline__ void dense_rows(const PropArgs<T>& a, const DenseScratch<T>& sc, long long gw, unsigned int* win) {
+    const unsigned n_fb = __ldcg(&a.st->fb_count);
     const int lane = lane_id();
-    const long long gw = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);
     T* acc = sc.acc + gw * sc.n;
     T* oldv = sc.oldv + gw * sc.n;
     int32_t* ord = sc.ord + gw * sc.n;
     uint32_t* tbits = sc.tbits + gw * sc.words;
     uint32_t* kbits = sc.kbits + gw * sc.words;
-    const bool cut_on = a.st->cut_on != 0;
-    const T cut = (T)a.st->cut;
-    const bool pred_valid = a.st->pred_valid != 0;
-    const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)a.st->pred_prefix0;
+    const bool cut_on = __ldcg(&a.st->cut_on) != 0;
+    const T cut = (T)__ldcg(&a.st->cut);
+    const bool pred_valid = __ldcg(&a.st->pred_valid) != 0;
+    const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)__ldcg(&a.st->pred_prefix0);
     WarpTotals wt;
     totals_init(wt);
 
@@ -847,8 +801,23 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T>
         __syncwarp();
     }
     totals_flush(a, wt);
+}
+
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T> a, DenseScratch<T> sc) {
+    __shared__ unsigned int win[kHistWin];
+    if (a.st->done) return;
+    if (a.st->fb_count == 0) {
+        // the usual case: no row was deferred, the step's histogram is already complete.  No CTA has row
+        // work, so no "last CTA" is needed: CTA 0 scans, the others leave at once.
+        if (a.fused_select && blockIdx.x == 0) scan_tail<T, WARPS * 32>(a.st, a.hist);
+        return;
+    }
+    for (int i = threadIdx.x; i < kHistWin; i += WARPS * 32) win[i] = 0u;
     __syncthreads();
-    if (a.hist && n_fb) hist_window_flush<T>(a.hist, win);
+    dense_rows<T>(a, sc, (long long)blockIdx.x * WARPS + (threadIdx.x >> 5), win);
+    __syncthreads();
+    if (a.hist) hist_window_flush<T>(a.hist, win);
 
     // ---- fused select (unsharded walk) when rows were deferred: the histogram is complete only now
     if (a.fused_select && !a.st->scan_done && last_block(&a.st->tick_dense)) scan_tail<T, WARPS * 32>(a.st, a.hist);

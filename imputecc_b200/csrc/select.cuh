@@ -36,10 +36,18 @@ __device__ __noinline__ void scan_level(WalkState* st, const unsigned long long*
     __shared__ unsigned long long s_total;
     const unsigned long long* h = hist + (size_t)level * kSelectBins;
     const int t = threadIdx.x;
-    unsigned long long c[BPT];
+    // a thread's bins stay in registers when there are few of them; small CTAs (many bins per thread)
+    // re-read them instead of holding a 128-entry register array
+    constexpr bool kInRegs = BPT <= 32;
+    unsigned long long c[kInRegs ? BPT : 1];
     unsigned long long mine = 0;
+    if constexpr (kInRegs) {
 #pragma unroll
-    for (int i = 0; i < BPT; ++i) { c[i] = __ldcg(h + t * BPT + i); mine += c[i]; }
+        for (int i = 0; i < BPT; ++i) { c[i] = __ldcg(h + t * BPT + i); mine += c[i]; }
+    } else {
+#pragma unroll 8
+        for (int i = 0; i < BPT; ++i) mine += __ldcg(h + t * BPT + i);
+    }
     unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -89,14 +97,27 @@ __device__ __noinline__ void scan_level(WalkState* st, const unsigned long long*
     __syncthreads();                                            // all reads precede the single write
     if (target >= excl && target < excl + mine) {          // exactly one thread: the bin lies in its range
         unsigned long long run = excl;
+        if constexpr (kInRegs) {
 #pragma unroll
-        for (int i = 0; i < BPT; ++i) {
-            if (target >= run && target < run + c[i]) {
-                st->below = below0 + run;
-                st->prefix = (prefix0 << kSelectBits) | (unsigned long long)(t * BPT + i);
-                st->bin_count = c[i];
+            for (int i = 0; i < BPT; ++i) {
+                if (target >= run && target < run + c[i]) {
+                    st->below = below0 + run;
+                    st->prefix = (prefix0 << kSelectBits) | (unsigned long long)(t * BPT + i);
+                    st->bin_count = c[i];
+                }
+                run += c[i];
             }
-            run += c[i];
+        } else {
+            for (int i = 0; i < BPT; ++i) {
+                const unsigned long long ci = __ldcg(h + t * BPT + i);
+                if (target < run + ci) {
+                    st->below = below0 + run;
+                    st->prefix = (prefix0 << kSelectBits) | (unsigned long long)(t * BPT + i);
+                    st->bin_count = ci;
+                    break;
+                }
+                run += ci;
+            }
         }
     }
     __syncthreads();
@@ -159,19 +180,30 @@ struct FinishArgs {
     int32_t do_select;                    // 0 on step 0 (utility.py:286)
 };
 
+// Shared-memory scratch the finish step needs (carved from the caller's buffer, 16-byte aligned).
+constexpr size_t kFinishScratchBytes = sizeof(unsigned long long) * (kCandSmem + 4 + 32 + 4) + sizeof(unsigned int) * 256 +
+                                       sizeof(int) * 4 + ((sizeof(WalkState) + 15) / 16) * 16 + 64;
+
 template <typename T>
-__device__ void finish_step_body(const FinishArgs& a) {
+__device__ __noinline__ void finish_step_body(const FinishArgs& a, unsigned char* scratch) {
     typedef KeyOf<T> KO;
     typedef typename KO::type K;
-    __shared__ unsigned long long sk[kCandSmem];
-    __shared__ unsigned int sh_hist[256];
-    __shared__ unsigned long long sh_io[4];
-    __shared__ unsigned long long wbest[32];
-    __shared__ unsigned long long s_xk, s_xk1, s_total, s_succ;
-    __shared__ int s_have1, s_ovf;
+    unsigned long long* sk = reinterpret_cast<unsigned long long*>(scratch);
+    unsigned long long* sh_io = sk + kCandSmem;
+    unsigned long long* wbest = sh_io + 4;
+    unsigned long long* s64 = wbest + 32;                 // s_xk, s_xk1, s_total, s_succ
+    unsigned int* sh_hist = reinterpret_cast<unsigned int*>(s64 + 4);
+    int* s32 = reinterpret_cast<int*>(sh_hist + 256);     // s_have1, s_ovf
+    WalkState* s_state_p = reinterpret_cast<WalkState*>(s32 + 4);
+#define s_xk s64[0]
+#define s_xk1 s64[1]
+#define s_total s64[2]
+#define s_succ s64[3]
+#define s_have1 s32[0]
+#define s_ovf s32[1]
     // the walk state is worked on in shared memory (one coalesced read, one coalesced write) instead of
     // through dozens of dependent L2 round trips by thread 0; no other CTA touches it at this point
-    __shared__ WalkState s_state;
+    WalkState& s_state = *s_state_p;
     WalkState* const gst = a.st;
     const int t = threadIdx.x;
     {
@@ -352,19 +384,23 @@ __device__ void finish_step_body(const FinishArgs& a) {
     for (int i = t; i < kSelectLevels * kSelectBins + kXExtras; i += blockDim.x) a.hist[i] = 0ull;
 }
 
+#undef s_xk
+#undef s_xk1
+#undef s_total
+#undef s_succ
+#undef s_have1
+#undef s_ovf
+
+// One histogram pass over the value array by the whole grid: level 0 counts the top 12 key bits of every
+// value, level 1 the next 12 bits of the values inside level-0 bin `prefix`.  `sh` is a 4096-bin
+// shared-memory histogram private to the CTA; it is flushed with one atomic per non-empty bin.
 template <typename T>
-__global__ void __launch_bounds__(512) select_hist_kernel(const T* __restrict__ vals, WalkState* st,
-                                                          unsigned long long* __restrict__ hist, int level,
-                                                          int fused_tail) {
+__device__ __noinline__ void hist_pass(const T* vals, long long n, typename KeyOf<T>::type prefix, int level,
+                                          unsigned int* sh, unsigned long long* hist) {
     typedef KeyOf<T> KO;
     typedef typename KO::type K;
-    __shared__ unsigned int sh[kSelectBins];
-    if (st->done) return;
-    if (fused_tail && st->hist1_ready) return;      // the propagate epilogue already filled and scanned this level
     for (int i = threadIdx.x; i < kSelectBins; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
-    const long long n = (long long)st->cursor;
-    const K prefix = (K)st->prefix;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
         T vv[4];
@@ -389,6 +425,15 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const T* __restrict__ 
         unsigned int c = sh[i];
         if (c) atomicAdd(&out[i], (unsigned long long)c);
     }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) select_hist_kernel(const T* vals, WalkState* st, unsigned long long* __restrict__ hist,
+                                                          int level, int fused_tail) {
+    __shared__ unsigned int sh[kSelectBins];
+    if (st->done) return;
+    if (fused_tail && st->hist1_ready) return;      // the propagate epilogue already filled and scanned this level
+    hist_pass<T>(vals, (long long)st->cursor, (typename KeyOf<T>::type)st->prefix, level, sh, hist);
     if (fused_tail && last_block(&st->tick_hist1)) scan_level<T, 512>(st, hist, level);
 }
 
@@ -400,16 +445,12 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(WalkState* st, const 
 }
 
 // Candidate block layout (uint64): [0] count, [1] smallest key above the candidate bin, [2..] keys.
-// fused_finish (unsharded walks): the last CTA to finish runs the step's finish logic.
+// One pass over the value array by the whole grid.
 template <typename T>
-__global__ void __launch_bounds__(512) select_gather_kernel(const T* __restrict__ vals, WalkState* st,
-                                                            unsigned long long* __restrict__ block,
-                                                            unsigned long long cand_cap, int fused, FinishArgs fin) {
+__device__ __noinline__ void gather_pass(const T* vals, long long n, typename KeyOf<T>::type prefix,
+                                            unsigned long long* block, unsigned long long cand_cap) {
     typedef KeyOf<T> KO;
     typedef typename KO::type K;
-    if (st->done) return;
-    const long long n = (long long)st->cursor;
-    const K prefix = (K)st->prefix;
     const long long stride = (long long)gridDim.x * blockDim.x;
     K best = ~(K)0;
     bool have = false;
@@ -435,13 +476,23 @@ __global__ void __launch_bounds__(512) select_gather_kernel(const T* __restrict_
     unsigned long long b64 = have ? (unsigned long long)best : ~0ull;
     b64 = warp_min(b64);
     if ((threadIdx.x & 31) == 0 && b64 != ~0ull) atomicMin(&block[1], b64);
-    if (fused && last_block(&st->tick_gather)) finish_step_body<T>(fin);
+}
+
+// fused (unsharded walks): the last CTA to finish runs the step's finish logic.
+template <typename T>
+__global__ void __launch_bounds__(512) select_gather_kernel(const T* vals, WalkState* st, unsigned long long* __restrict__ block,
+                                                            unsigned long long cand_cap, int fused, FinishArgs fin) {
+    __shared__ __align__(16) unsigned char scratch[kFinishScratchBytes];
+    if (st->done) return;
+    gather_pass<T>(vals, (long long)st->cursor, (typename KeyOf<T>::type)st->prefix, block, cand_cap);
+    if (fused && last_block(&st->tick_gather)) finish_step_body<T>(fin, scratch);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(1024) finish_step_kernel(FinishArgs a) {
+    __shared__ __align__(16) unsigned char scratch[kFinishScratchBytes];
     if (a.st->done) return;
-    finish_step_body<T>(a);
+    finish_step_body<T>(a, scratch);
 }
 
 // Sharded walk: publish this rank's step counters behind the level-0 histogram so that ONE

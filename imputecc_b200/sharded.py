@@ -101,11 +101,11 @@ def run_sharded_walk(phases, comm, perc, max_steps):
     """Drive utility.py:281-304 across the shards behind ``comm``; every rank issues the same sequence.
 
     ``phases`` is a CudaPhases (the CPU tests pass an object with the same methods)."""
-    from .crwr import next_row_hints
+    from .crwr import next_row_hints, poll_chunk
     issued = 0
     hints = next_row_hints(0, 0, perc, 0)
     while True:
-        chunk = 1 if issued < 2 else 4
+        chunk = min(poll_chunk(issued), 4)
         chunk = min(chunk, max_steps - issued)
         phases.set_row_hints(hints)
         for _ in range(chunk):

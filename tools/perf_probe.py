@@ -38,6 +38,9 @@ for rep in range(args.reps):
     ph = (_lib.C.c_double * 3)()
     lib.crwr_profile_phases(w.handle, ph)
     print("rep %d: %d steps, wall %.3f ms, propagate total %.3f ms over %d launches | phases: prop+dense %.3f hist1 %.3f gather+finish %.3f" % (rep, st.steps_done, wall * 1e3, tot.value, nl.value, ph[0], ph[1], ph[2]))
+pn = (_lib.C.c_uint64 * 8)()
+lib.crwr_phase_ns(w.handle, pn, w._stream())
+print("phase us (last walk): propagate %.1f | barrier %.1f | scan %.1f | barrier %.1f | l1+gather %.1f | barrier %.1f | finish %.1f | barrier %.1f" % tuple(x / 1e3 for x in pn))
 shape = (_lib.C.c_int64 * 8)()
 lib.crwr_get_shape(w.handle, shape)
 print("shape H %d limit %d kmax %d scap %d warps %d per_warp %d grid %d sms %d" % tuple(shape))
