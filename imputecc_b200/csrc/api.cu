@@ -146,6 +146,7 @@ struct crwr_handle_s {
     WalkState* h_state = nullptr;               // pinned host mirror of the device state (polls)
     long long hint_len = -1, hint_kept = -1;    // last sizing hints (configure_shape is skipped when unchanged)
     long long hint_len_eff = 128;               // expected longest product row
+    bool hist0_fused = false;                   // sharded step: level-0 histogram already filled by propagate
     bool profile = false;                       // CUDA events around every main propagate launch
     std::vector<cudaEvent_t> ev;                // start/end pairs
     std::vector<cudaEvent_t> marks;             // profile mode: step start + one event after each kernel of the step
@@ -262,6 +263,7 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     a.restart = (T)(float)h->rp;                // rp * I with I float32 (utility.py:278)
     a.hist = fused ? hist_ptr(h) : nullptr;
     a.fused_select = fused ? 1 : 0;
+    a.prefill_l1 = fused ? 1 : 0;
     // a warp reserves output space for a few rows at a time (zero-padded leftovers are skipped by the select)
     {
         long long ch = 3 * (long long)h->hint_len_eff;
@@ -281,6 +283,7 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
 template <typename T>
 int launch_propagate(crwr_handle_s* h, int parity, bool fused, cudaStream_t st) {
     PropArgs<T> a = prop_args<T>(h, parity, fused);
+    if (!fused && h->cfg.n_shards > 1 && h->hist0_fused) a.hist = hist_ptr(h);   // sharded: histogram only, no scan tail
     const int rows = a.n_rows;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
@@ -822,6 +825,8 @@ int32_t crwr_walk_enqueue(crwr_handle h, int32_t n_steps, void* stream) {
 
 int32_t crwr_step_propagate(crwr_handle h, void* stream) {
     STEP_PROLOGUE();
+    // steps >= 1: the level-0 histogram is filled by the propagate epilogue (crwr_step_hist(0) then has nothing to do)
+    h->hist0_fused = h->steps_enqueued >= 1;
     int e = f64 ? launch_propagate<double>(h, parity, false, st) : launch_propagate<float>(h, parity, false, st);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "propagate launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     pack_exchange_kernel<<<1, 32, 0, st>>>(h->at<WalkState>(h->L.state), h->at<unsigned long long>(h->L.xbuf));
@@ -831,6 +836,7 @@ int32_t crwr_step_propagate(crwr_handle h, void* stream) {
 int32_t crwr_step_hist(crwr_handle h, int32_t level, void* stream) {
     STEP_PROLOGUE();
     if (level < 0 || level >= kSelectLevels) CRWR_FAIL(CRWR_ERR_INVALID, "level out of range");
+    if (level == 0 && h->hist0_fused) return CRWR_OK;        // filled by the propagate epilogue
     int e = f64 ? launch_hist<double>(h, parity ^ 1, level, 0, st) : launch_hist<float>(h, parity ^ 1, level, 0, st);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "hist launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return CRWR_OK;
@@ -893,6 +899,7 @@ int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
     if (s.done && s.stop_reason == CRWR_STOP_RUNNING) out->stop_reason = CRWR_STOP_MAX_STEPS;
     // the host-side step counter follows the device: steps enqueued past the stop were skipped
     if (s.done) h->steps_enqueued = s.step;
+    if (s.debug_error) CRWR_FAIL(CRWR_ERR_STATE, "internal bounds check %d failed (CRWR_DEBUG_CHECKS build)", s.debug_error);
     if (s.capacity_overflow) CRWR_FAIL(CRWR_ERR_CAPACITY, "iterate buffer overflow (capacity %lld entries)", (long long)h->cfg.iterate_cap);
     if (s.select_overflow) CRWR_FAIL(CRWR_ERR_CAPACITY, "percentile candidate buffer overflow");
     return CRWR_OK;

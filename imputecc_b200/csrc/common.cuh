@@ -111,6 +111,8 @@ struct WalkState {
     int32_t hist1_ready;               // level-1 histogram already holds the counts of the selected level-0 bin
     unsigned int tick_dense, tick_hist1, tick_gather;   // last-CTA tickets
     unsigned int tick_prop;
+    int32_t debug_error;               // CRWR_DEBUG_CHECKS builds: highest failed bounds-check code (0 = none)
+    int32_t pad4;
     unsigned long long phase_ns[8];    // persistent kernel: summed nanoseconds per phase (CTA 0's view), diagnostics
     int32_t scan_done;                 // the level scans of this step already ran (in the propagate kernel's last CTA)
     int32_t pad3;
@@ -121,6 +123,14 @@ constexpr int kXSq0 = 0, kXSq1 = 1, kXSq2 = 2, kXNnzIn = 3, kXNnzNew = 4, kXCapO
 constexpr int kXExtras = 8;
 // Candidate block: [count, successor key, keys...] (uint64).
 constexpr int kCandHeader = 2;
+
+// Bounds checks of our own (compute-sanitizer is closed on this pool): a -DCRWR_DEBUG_CHECKS build
+// records the highest failed check code in the walk state instead of trapping; crwr_walk_poll reports it.
+#ifdef CRWR_DEBUG_CHECKS
+#define CRWR_CHECK(st, cond, code) do { if (!(cond)) atomicMax(&(st)->debug_error, (int)(code)); } while (0)
+#else
+#define CRWR_CHECK(st, cond, code) do { } while (0)
+#endif
 
 template <typename T>
 struct IterBuf {
@@ -178,6 +188,34 @@ __device__ __forceinline__ void warp_sort_pairs(K* key, V* val, int n) {
             __syncwarp();
         }
     }
+}
+
+// Same, for n <= 32 pairs living in global memory: one pair per lane, sorted in registers with shuffles
+// (the memory-resident network above costs a round trip per stage when the arrays are in global memory).
+template <typename V>
+__device__ __forceinline__ void warp_sort_pairs32(int32_t* key, V* val, int n) {
+    const int lane = lane_id();
+    int32_t k = lane < n ? key[lane] : 0x7fffffff;
+    V v = lane < n ? val[lane] : (V)0;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            const int32_t ok = __shfl_xor_sync(kFull, k, j);
+            const V ov = __shfl_xor_sync(kFull, v, j);
+            const bool asc = (lane & size) == 0;
+            const bool lower = (lane & j) == 0;
+            const bool take_other = (lower == asc) ? (ok < k) : (ok > k);     // keys are unique (padding excepted)
+            if (take_other) { k = ok; v = ov; }
+        }
+    }
+    if (lane < n) { key[lane] = k; val[lane] = v; }
+}
+
+template <typename K, typename V>
+__device__ __forceinline__ void warp_sort_pairs_any(K* key, V* val, int n) {
+    if (n <= 32) warp_sort_pairs32(key, val, n);
+    else warp_sort_pairs(key, val, n);
 }
 
 // numpy's pairwise summation as np.add.reduceat applies it to one contiguous segment:

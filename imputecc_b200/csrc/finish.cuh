@@ -58,7 +58,7 @@ __global__ void result_write_kernel(IterBuf<T> buf, const WalkState* __restrict_
         w += __popc(m);
     }
     __syncwarp();
-    if (w > 1) warp_sort_pairs(out_cols + base, out_vals + base, w);
+    if (w > 1) warp_sort_pairs_any(out_cols + base, out_vals + base, w);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -116,7 +116,7 @@ __global__ void sym_sort_count_kernel(int m, const int64_t* __restrict__ indptr,
     const int lane = lane_id();
     const long long ts = sc.t_ptr[row];
     const int tn = (int)(sc.t_ptr[row + 1] - ts);
-    if (tn > 1) warp_sort_pairs(sc.t_col + ts, sc.t_val + ts, tn);
+    if (tn > 1) warp_sort_pairs_any(sc.t_col + ts, sc.t_val + ts, tn);
     __syncwarp();
     const long long as = indptr[row];
     const int an = (int)(indptr[row + 1] - as);
@@ -174,7 +174,7 @@ __global__ void sym_merge_kernel(int m, const int64_t* __restrict__ indptr, cons
         w += __popc(mk);
     }
     __syncwarp();
-    if (w > 1) warp_sort_pairs(out_cols + base, out_vals + base, w);
+    if (w > 1) warp_sort_pairs_any(out_cols + base, out_vals + base, w);
     __syncwarp();
     if (lane == 0) {
         T d = (T)0;

@@ -39,6 +39,7 @@ struct PropArgs {
     int32_t fused_select;       // 1: the last CTA of the large-row kernel scans the histograms
     int32_t chunk;              // entries a warp reserves from the product buffer at a time
     int32_t row_chunk;          // rows a warp takes from the row counter at a time
+    int32_t prefill_l1;         // 1: also count level 1 for the level-0 bin predicted from the previous cut
 };
 
 // Fused select, unsharded walk: once every value of the step is in the level-0 histogram, one CTA locates
@@ -146,6 +147,7 @@ __device__ __forceinline__ void write_row(const PropArgs<T>& a, WarpTotals& w, i
         unsigned m = __ballot_sync(kFull, nz);
         if (nz) {
             long long o = base + written + __popc(m & lanemask_lt());
+            CRWR_CHECK(a.st, o >= 0 && o < a.out_cap, 6);
             a.out.cols[o] = c;
             a.out.vals[o] = v;
         }
@@ -197,7 +199,7 @@ __device__ __forceinline__ void hist_values(unsigned long long* hist, unsigned i
     if (valid && (peers & lanemask_lt()) == 0u) {
         const unsigned w = bin0 - (unsigned)HistWindow<T>::base;
         if (w < (unsigned)kHistWin) atomicAdd(&win[w], (unsigned)__popc(peers));
-        else atomicAdd(&hist[bin0], (unsigned long long)__popc(peers));
+        else atomicAdd(&hist[bin0 & (kSelectBins - 1)], (unsigned long long)__popc(peers));
     }
     if (valid && pred_valid && (key >> (KO::bits - kSelectBits)) == pred0)
         atomicAdd(&hist[kSelectBins + ((unsigned)(key >> (KO::bits - 2 * kSelectBits)) & (kSelectBins - 1))], 1ull);
@@ -348,7 +350,7 @@ __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropS
 
     const bool cut_on = __ldcg(&a.st->cut_on) != 0;
     const T cut = (T)__ldcg(&a.st->cut);
-    const bool pred_valid = __ldcg(&a.st->pred_valid) != 0;
+    const bool pred_valid = a.prefill_l1 && __ldcg(&a.st->pred_valid) != 0;
     const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)__ldcg(&a.st->pred_prefix0);
     const int32_t* __restrict__ pcols = a.p_cols;
     const T* __restrict__ pvals = a.p_vals;
@@ -394,6 +396,7 @@ __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropS
             const T q = kval[idx];
             const int32_t* gc = pcols + ps;
             const T* gv = pvals + ps;
+            CRWR_CHECK(a.st, off + len <= SCAP, 3);
             for (int e = 0; e < len; ++e) {
                 cp_async4(dc + off + e, gc + e);
                 cp_async_val(dv + off + e, gv + e);
@@ -432,7 +435,7 @@ __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropS
                 const bool keep = (e < len) && (!cut_on || v[u] > cut);
                 const unsigned m = __ballot_sync(kFull, keep);
                 const int pos = nk + __popc(m & lanemask_lt());
-                if (keep && pos < KMAX) { kcol[pos] = c[u]; kval[pos] = v[u]; }
+                if (keep && pos < KMAX) { CRWR_CHECK(a.st, c[u] >= 0, 4); kcol[pos] = c[u]; kval[pos] = v[u]; }
                 nk += __popc(m);
             }
         }
@@ -450,6 +453,7 @@ __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropS
             }
             for (int idx = lane; idx < nk; idx += 32) {
                 const int k = kcol[idx];
+                CRWR_CHECK(a.st, k >= 0, 5);
                 const int ps = __ldg(a.p_indptr + k);
                 kps[idx] = ps;
                 klen[idx] = __ldg(a.p_indptr + k + 1) - ps;
@@ -499,7 +503,7 @@ __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropS
                         slot = hash_slot(j, H);
                         for (;;) {
                             int32_t kk = tkey[slot];
-                            while (kk != j && kk != -1) kk = tkey[++slot];     // read-only probe
+                            while (kk != j && kk != -1) { ++slot; CRWR_CHECK(a.st, slot < (uint32_t)HT, 1); kk = tkey[slot]; }   // read-only probe
                             if (kk == j) { acc = add_rn(tval[slot], prod); break; }
                             if (slot == (uint32_t)(HT - 1)) { slot = 0; continue; }   // sentinel slot: wrap
                             if (atomicCAS(&tkey[slot], -1, j) == -1) { is_new = true; break; }
@@ -519,6 +523,7 @@ __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropS
                     if (leader) tval[slot] = acc;
                     const unsigned nm = __ballot_sync(kFull, is_new);
                     if (nm) {
+                        CRWR_CHECK(a.st, count + 32 <= LIMIT + 32, 2);
                         if (is_new) ord[count + __popc(nm & lanemask_lt())] = (uint16_t)slot;
                         count += __popc(nm);
                     }
@@ -681,7 +686,7 @@ __device__ __noinline__ void dense_rows(const PropArgs<T>& a, const DenseScratch
     uint32_t* kbits = sc.kbits + gw * sc.words;
     const bool cut_on = __ldcg(&a.st->cut_on) != 0;
     const T cut = (T)__ldcg(&a.st->cut);
-    const bool pred_valid = __ldcg(&a.st->pred_valid) != 0;
+    const bool pred_valid = a.prefill_l1 && __ldcg(&a.st->pred_valid) != 0;
     const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)__ldcg(&a.st->pred_prefix0);
     WarpTotals wt;
     totals_init(wt);

@@ -126,7 +126,7 @@ __global__ void transition_colsum_kernel(long long n, TransitionScratch sc) {
     if (col >= n) return;
     const int s = sc.col_ptr[col];
     const int len = sc.col_ptr[col + 1] - s;
-    if (len > 1) warp_sort_pairs(sc.csc_row + s, sc.csc_val + s, len);
+    if (len > 1) warp_sort_pairs_any(sc.csc_row + s, sc.csc_val + s, len);
     __syncwarp();
     if (lane_id() == 0) {
         double sum = 0.0;
@@ -177,7 +177,7 @@ __global__ void transition_fill_kernel(const int64_t* __restrict__ indptr, const
         w += 1;
     }
     __syncwarp();
-    if (w > 1) warp_sort_pairs(p_cols + base, sc.row_val + base, w);
+    if (w > 1) warp_sort_pairs_any(p_cols + base, sc.row_val + base, w);
     __syncwarp();
     const double scl = sc.scale[rn];
     for (int i = lane; i < w; i += 32) p_vals[base + i] = (T)mul_rn(scl, sc.row_val[base + i]);   // :118-119

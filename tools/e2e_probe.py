@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Developer probe: host-side time breakdown of crwr_impute()."""
+"""Developer probe: host-side time breakdown of crwr_impute() (same statements, timed)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,20 +7,22 @@ import torch
 import scipy.sparse as sp
 import imputecc_b200 as pkg
 from imputecc_b200 import crwr, synth, _lib
-import ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import pinned_csr
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "c3_sparse"
-M, idx = synth.make_workload(synth.WORKLOADS[wl])
+M0, idx = synth.make_workload(synth.WORKLOADS[wl])
+M = pinned_csr(M0)
 n, m = M.shape[0], idx.size
 dev = torch.device("cuda:0")
 
 def T():
     torch.cuda.synchronize(); return time.perf_counter()
 
-for rep in range(4):
+for rep in range(5):
     t = [T()]
-    crwr.validate_inputs(M, idx, 0.5, 80); t.append(T())
-    Mc = sp.csr_matrix(M); _ = Mc.has_canonical_format; t.append(T())
+    crwr.validate_inputs(M, idx, 0.5, 80, check_values=False); t.append(T())
+    _ = M.has_canonical_format; t.append(T())
     noo = crwr.markers_first_order(n, idx); t.append(T())
     w = pkg.Walker(n, m, dtype=np.float32, device=dev, transition_nnz_cap=int(M.nnz) + n); t.append(T())
     w.build_transition(M.indptr, M.indices, M.data, noo); t.append(T())
@@ -31,4 +33,5 @@ for rep in range(4):
     w.close(); t.append(T())
     names = ["validate", "canonical", "order", "create", "transition", "walk", "result", "symmetrise", "download", "close"]
     print("rep %d total %.3f ms | " % (rep, 1e3 * (t[-1] - t[0])) + " ".join("%s %.3f" % (nm, 1e3 * (b - a)) for nm, a, b in zip(names, t, t[1:])))
-print("workspace MB", w.cap, )
+t0 = T(); E = pkg.crwr_impute(M, idx, 0.5, 80, device=dev); t1 = T()
+print("crwr_impute call: %.3f ms" % (1e3 * (t1 - t0)))
