@@ -273,9 +273,10 @@ def main():
 
     steps_per_walk = len(trace)
     if world == 1:
-        kern_ms, kern_launches, _ = profiled_walk(1)
-        prop_ms, _, phases = profiled_walk(0)          # pass B: one launch per phase -> propagate_kernel alone
-        walker.set_mode(1)
+        default_mode = int(os.environ.get("CRWR_WALK_MODE", "0"))
+        kern_ms, kern_launches, _ = profiled_walk(default_mode)
+        prop_ms, _, phases = profiled_walk(0)          # one launch per phase -> propagate_kernel alone
+        walker.set_mode(default_mode)
         persistent = kern_launches < steps_per_walk     # fewer launches than steps: chunks ran as one kernel each
     else:
         lib.crwr_profile(walker.handle, 1)

@@ -30,6 +30,7 @@ DEFAULT_TOL = 0.01          # imputation.py:120
 DEFAULT_MAX_STEPS = 500     # utility.py:281
 # walk steps enqueued between two status polls (steps after the stop rule fired are skipped on the device)
 POLL_EVERY = int(__import__("os").environ.get("CRWR_POLL_EVERY", "16"))
+PERSISTENT_POLL_EVERY = 16
 _m = __import__("os").environ.get("CRWR_WALK_MODE")
 WALK_MODE = int(_m) if _m is not None else None     # developer override of crwr_set_mode
 
@@ -130,17 +131,19 @@ def default_iterate_cap(n_rows: int, n_contigs: int) -> int:
     return int(min(n_rows * n_contigs, max(1 << 22, 2048 * n_rows)))
 
 
-def poll_chunk(issued: int) -> int:
+def poll_chunk(issued: int, persistent: bool = False) -> int:
     """Walk steps to enqueue before the next status poll.
 
     Steps 0 and 1 change the row shapes most, so the kernel sizing hints are refreshed after each;
-    after step 3 the kept share has been observed and the walk runs in long chunks (steps enqueued
-    after the stop rule fired are skipped on the device)."""
+    after step 3 the kept share has been observed and the walk runs in long chunks.  Steps enqueued
+    after the stop rule fired are skipped on the device (three empty launches each, ~7 us, with one
+    launch per phase; free inside the persistent kernel) - cheaper than an extra poll (~28 us: stream
+    sync, status copy, relaunch gap) for walks of the usual 13-19 steps."""
     if issued < 2:
         return 1
     if issued < 4:
         return 2
-    return POLL_EVERY
+    return PERSISTENT_POLL_EVERY if persistent else POLL_EVERY
 
 
 def next_row_hints(max_row_len: int, max_kept: int, perc: float, issued: int):
@@ -202,6 +205,7 @@ class Walker:
         self.regrows = 0
         self._walk_args = None
         self.hint_override = None      # tests pin the kernel sizing through this
+        self.mode = 0                  # crwr_set_mode: 0 = one launch per phase, 1 = persistent kernel
         self._create()
 
     # -- plumbing ---------------------------------------------------------------------------
@@ -319,8 +323,9 @@ class Walker:
 
     # -- the walk -----------------------------------------------------------------------------
     def set_mode(self, mode: int):
-        """1: persistent cooperative kernel per chunk of steps (default); 0: one launch per phase."""
+        """0: one launch per phase (default); 1: persistent cooperative kernel per chunk of steps."""
         _lib.check(self.lib.crwr_set_mode(self.handle, int(mode)))
+        self.mode = int(mode)
 
     def walk_init(self, rp, perc, tol=DEFAULT_TOL, max_steps=DEFAULT_MAX_STEPS):
         self._walk_args = (float(rp), float(perc), float(tol), int(max_steps))
@@ -352,7 +357,7 @@ class Walker:
         hints = next_row_hints(0, 0, perc, 0)
         while True:
             # steps 0 and 1 change the row shapes most: poll after each; later run four at a time
-            chunk = poll_chunk(issued)
+            chunk = poll_chunk(issued, self.mode == 1)
             chunk = min(chunk, max_steps - issued)
             self.set_row_hints(*hints)
             _lib.check(lib.crwr_walk_enqueue(h, chunk, self._stream()))

@@ -136,8 +136,11 @@ struct crwr_handle_s {
     int steps_enqueued;
     PropShape shape;                // run-time sizing of the main propagate kernel
     int grid;                       // its persistent grid size
-    int mode = 1;                   // 1: one cooperative kernel per chunk of steps; 0: one launch per phase
-    int mode_next = 1;              // takes effect at the next crwr_walk_init
+    // 0 (default): one launch per phase.  1: one cooperative kernel per chunk of steps - measured equal for
+    // float32 small-row workloads and 10-15 % slower for float64 (small CTAs make CTA 0's serial scan/finish
+    // phases slower), so it is opt-in.
+    int mode = 0;
+    int mode_next = 0;              // takes effect at the next crwr_walk_init
     bool coop_ok = false;           // device supports cooperative launches
     int coop_grid = 0;              // co-resident CTAs of walk_chunk_kernel for the current shape
     size_t coop_smem = 0;

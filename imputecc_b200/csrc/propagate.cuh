@@ -323,7 +323,9 @@ __device__ __forceinline__ void warp_sort_kept_regs(int32_t* kcol, T* kval, T* s
 
 // One walk step's propagation for the rows of this shard (all CTAs of the grid cooperate through the
 // row counter).  Called by every thread of every CTA; smem_raw is the CTA's dynamic shared memory.
-template <typename T>
+// COHERENT: read the operand iterate with ordinary loads (required inside the persistent kernel, which
+// rewrites that buffer two steps later); otherwise through the read-only path.
+template <typename T, bool COHERENT>
 __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropShape& sh, unsigned char* smem_raw) {
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
@@ -427,7 +429,10 @@ __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropS
             for (int u = 0; u < 4; ++u) {
                 const int e = b + u * 32 + lane;
                 c[u] = 0; v[u] = (T)0;
-                if (e < len) { c[u] = rc[e]; v[u] = rv[e]; }
+                if (e < len) {
+                    if (COHERENT) { c[u] = rc[e]; v[u] = rv[e]; }
+                    else { c[u] = __ldg(rc + e); v[u] = __ldg(rv + e); }
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -629,7 +634,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape sh) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (a.st->done) return;
-    propagate_rows<T>(a, sh, smem_raw);
+    propagate_rows<T, false>(a, sh, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -676,7 +681,7 @@ __device__ __forceinline__ void dense_accumulate_row_of_p(const PropArgs<T>& a, 
 // Rows deferred by the main kernel, one per warp at a time; gw = this warp's slot in the dense scratch.
 // Ends with the warp's totals published; the caller flushes the histogram window after a CTA barrier.
 template <typename T>
-__device__ __noinline__ void dense_rows(const PropArgs<T>& a, const DenseScratch<T>& sc, long long gw, unsigned int* win) {
+__device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScratch<T>& sc, long long gw, unsigned int* win) {
     const unsigned n_fb = __ldcg(&a.st->fb_count);
     const int lane = lane_id();
     T* acc = sc.acc + gw * sc.n;

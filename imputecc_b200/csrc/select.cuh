@@ -185,7 +185,7 @@ constexpr size_t kFinishScratchBytes = sizeof(unsigned long long) * (kCandSmem +
                                        sizeof(int) * 4 + ((sizeof(WalkState) + 15) / 16) * 16 + 64;
 
 template <typename T>
-__device__ __noinline__ void finish_step_body(const FinishArgs& a, unsigned char* scratch) {
+__device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned char* scratch) {
     typedef KeyOf<T> KO;
     typedef typename KO::type K;
     unsigned long long* sk = reinterpret_cast<unsigned long long*>(scratch);
@@ -395,7 +395,7 @@ __device__ __noinline__ void finish_step_body(const FinishArgs& a, unsigned char
 // value, level 1 the next 12 bits of the values inside level-0 bin `prefix`.  `sh` is a 4096-bin
 // shared-memory histogram private to the CTA; it is flushed with one atomic per non-empty bin.
 template <typename T>
-__device__ __noinline__ void hist_pass(const T* vals, long long n, typename KeyOf<T>::type prefix, int level,
+__device__ __forceinline__ void hist_pass(const T* __restrict__ vals, long long n, typename KeyOf<T>::type prefix, int level,
                                           unsigned int* sh, unsigned long long* hist) {
     typedef KeyOf<T> KO;
     typedef typename KO::type K;
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(WalkState* st, const 
 // Candidate block layout (uint64): [0] count, [1] smallest key above the candidate bin, [2..] keys.
 // One pass over the value array by the whole grid.
 template <typename T>
-__device__ __noinline__ void gather_pass(const T* vals, long long n, typename KeyOf<T>::type prefix,
+__device__ __forceinline__ void gather_pass(const T* __restrict__ vals, long long n, typename KeyOf<T>::type prefix,
                                             unsigned long long* block, unsigned long long cand_cap) {
     typedef KeyOf<T> KO;
     typedef typename KO::type K;

@@ -53,6 +53,27 @@ __device__ __forceinline__ void grid_barrier(cg::grid_group& grid) {
     __syncthreads();
 }
 
+// Out-of-line copies of the phase bodies for the persistent kernel: inlined, the union of their register
+// needs (255) would cap the residency of the propagate phase; the stand-alone kernels keep them inline.
+template <typename T>
+__device__ __noinline__ void dense_rows_ni(const PropArgs<T>& a, const DenseScratch<T>& sc, long long gw, unsigned int* win) {
+    dense_rows<T>(a, sc, gw, win);
+}
+template <typename T>
+__device__ __noinline__ void hist_pass_ni(const T* vals, long long n, typename KeyOf<T>::type prefix, int level, unsigned int* sh,
+                                          unsigned long long* hist) {
+    hist_pass<T>(vals, n, prefix, level, sh, hist);
+}
+template <typename T>
+__device__ __noinline__ void gather_pass_ni(const T* vals, long long n, typename KeyOf<T>::type prefix, unsigned long long* block,
+                                            unsigned long long cand_cap) {
+    gather_pass<T>(vals, n, prefix, block, cand_cap);
+}
+template <typename T>
+__device__ __noinline__ void finish_step_ni(const FinishArgs& a, unsigned char* scratch) {
+    finish_step_body<T>(a, scratch);
+}
+
 template <typename T>
 __device__ __forceinline__ void scan_tail_any(WalkState* st, unsigned long long* hist) {
     switch (blockDim.x) {
@@ -92,7 +113,7 @@ __global__ void __launch_bounds__(256) walk_chunk_kernel(WalkChunkArgs<T> w) {
         a.hist = do_select ? w.hist : nullptr;
         a.fused_select = 0;
 
-        propagate_rows<T>(a, w.shape, smem_raw);
+        propagate_rows<T, true>(a, w.shape, smem_raw);
         PHASE_MARK(0)
         grid_barrier(grid);
         PHASE_MARK(1)
@@ -102,7 +123,7 @@ __global__ void __launch_bounds__(256) walk_chunk_kernel(WalkChunkArgs<T> w) {
             for (int i = threadIdx.x; i < kHistWin; i += blockDim.x) win[i] = 0u;
             __syncthreads();
             const long long gw = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
-            if (gw < w.dense_warps) dense_rows<T>(a, w.dense, gw, win);
+            if (gw < w.dense_warps) dense_rows_ni<T>(a, w.dense, gw, win);
             __syncthreads();
             if (a.hist) hist_window_flush<T>(a.hist, win);
             grid_barrier(grid);
@@ -114,13 +135,13 @@ __global__ void __launch_bounds__(256) walk_chunk_kernel(WalkChunkArgs<T> w) {
             grid_barrier(grid);
             PHASE_MARK(3)
             if (!ld_state(&st->hist1_ready)) {                  // the level-1 prediction missed: one more pass
-                hist_pass<T>(a.out.vals, (long long)ld_state(&st->cursor), (typename KeyOf<T>::type)ld_state(&st->prefix), 1,
+                hist_pass_ni<T>(a.out.vals, (long long)ld_state(&st->cursor), (typename KeyOf<T>::type)ld_state(&st->prefix), 1,
                              reinterpret_cast<unsigned int*>(smem_raw), w.hist);
                 grid_barrier(grid);
                 if (blockIdx.x == 0) scan_level_any<T>(st, w.hist, 1);
                 grid_barrier(grid);
             }
-            gather_pass<T>(a.out.vals, (long long)ld_state(&st->cursor), (typename KeyOf<T>::type)ld_state(&st->prefix),
+            gather_pass_ni<T>(a.out.vals, (long long)ld_state(&st->cursor), (typename KeyOf<T>::type)ld_state(&st->prefix),
                            w.cand_block, w.cand_cap);
             PHASE_MARK(4)
             grid_barrier(grid);
@@ -129,7 +150,7 @@ __global__ void __launch_bounds__(256) walk_chunk_kernel(WalkChunkArgs<T> w) {
         if (blockIdx.x == 0) {
             FinishArgs f = w.fin;
             f.do_select = do_select ? 1 : 0;
-            finish_step_body<T>(f, smem_raw);
+            finish_step_ni<T>(f, smem_raw);
         }
         PHASE_MARK(6)
         grid_barrier(grid);

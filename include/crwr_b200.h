@@ -131,9 +131,9 @@ int32_t crwr_phase_ns(crwr_handle h, uint64_t* h_out8, void* stream);
 /* Current kernel sizing (diagnostics): {H, limit, kmax, scap, warps/CTA, smem bytes/warp, grid, SMs}. */
 int32_t crwr_get_shape(crwr_handle h, int64_t* h_out8);
 
-/* Execution mode of crwr_walk_enqueue: 1 (default where the device supports cooperative launches) runs a
- * chunk of steps as ONE persistent cooperative kernel with grid barriers between the phases of a step; 0
- * launches one kernel per phase (always used by the sharded walk).  Results are identical.  Takes effect at
+/* Execution mode of crwr_walk_enqueue: 0 (default) launches one kernel per phase of a step (always used by the
+ * sharded walk); 1 runs a chunk of steps as ONE persistent cooperative kernel with grid barriers between the
+ * phases (small-row shapes only; measured no faster on B200).  Results are identical.  Takes effect at
  * the next crwr_walk_init. */
 int32_t crwr_set_mode(crwr_handle h, int32_t mode);
 

@@ -265,3 +265,22 @@ def test_bad_contact_values_are_rejected_on_the_device(cuda_device):
         B.data[7] = bad
         with pytest.raises(ValueError, match="finite and non-negative"):
             pkg.crwr_impute(B, np.array([3, 9, 40]), 0.5, 80, device=cuda_device)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_persistent_cooperative_kernel_mode_is_bit_identical(cuda_device, dtype):
+    """crwr_set_mode(1): a chunk of steps as one cooperative kernel with grid barriers - same bits, same steps."""
+    M, idx = synth.make_workload(synth.Workload("pm", 5000, 800, 100, 16))
+    n, m = M.shape[0], idx.size
+    outs = []
+    for mode in (0, 1):
+        w = pkg.Walker(n, m, dtype=dtype, device=cuda_device, transition_nnz_cap=M.nnz + n)
+        try:
+            w.build_transition(M.indptr, M.indices, M.data, pkg.markers_first_order(n, idx))
+            w.set_mode(mode)
+            st = w.walk(0.5, 80)
+            outs.append((int(st.steps_done), int(st.stop_reason), w.iterate(), [(t["nnz_in"], t["nnz_new"], t["cut"] if t["step"] else 0.0, t["delta"]) for t in w.trace()]))
+        finally:
+            w.close()
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and outs[0][3] == outs[1][3]
+    assert _bit_equal(outs[0][2], outs[1][2])
