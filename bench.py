@@ -172,7 +172,8 @@ def config_dict(wl, world, dtype):
     return {"workload": "%s: synthetic NormCC-like CSR, %d marker contigs on %d contigs, genome %d, intra-degree %d, "
                         "rwr-rp 0.5, rwr-thres 80" % (wl.name, wl.n_markers, wl.n_contigs, wl.genome_size, wl.intra_degree),
             "n_markers": wl.n_markers, "n_contigs": wl.n_contigs, "rp": 0.5, "perc": 80, "walk_dtype": dtype,
-            "parallelism": "restart rows sharded over %d GPU(s), transition matrix replicated" % world,
+            "parallelism": "restart rows sharded over %d GPU(s), transition matrix replicated%s" % (
+                world, "" if world == 1 else "; histogram/candidate exchange: %s" % os.environ.get("CRWR_SHARDED_EXCHANGE", "peer")),
             "l2": "L2 flushed (256 MiB write) between timed imputations"}
 
 
@@ -222,9 +223,16 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     comm = sharded.TorchComm(dist, dist.group.WORLD) if world > 1 else None
 
+    use_peer = world > 1 and sharded.peer_exchange_available(dist, dist.group.WORLD)
+    peer = sharded.PeerExchange.get(dist, dist.group.WORLD, device) if use_peer else None
+
     def one_walk():
         if world == 1:
             return walker.walk(0.5, 80)
+        if use_peer:
+            peer.attach(walker)                 # fresh barrier epochs for this walk
+            walker.walk_init(0.5, 80)
+            return sharded.run_sharded_walk_peer(walker, 80, 500)
         walker.walk_init(0.5, 80)
         return sharded.run_sharded_walk(sharded.CudaPhases(walker), comm, 80, 500)
 

@@ -14,6 +14,7 @@
 #include "transition.cuh"
 #include "finish.cuh"
 #include "walk.cuh"
+#include "peer.cuh"
 
 using namespace crwr;
 
@@ -48,7 +49,7 @@ constexpr int kDenseWarpsPerCta = 4;
 struct Layout {
     size_t state, trace, p_indptr, p_cols, p_vals;
     size_t it_cols[2], it_vals[2], it_ptr[2], it_len[2];
-    size_t fb_rows, xbuf, cand, merged, counts, counts_scan, total;
+    size_t fb_rows, xbuf, cand, merged, gathered, counts, counts_scan, total;
     size_t d_acc, d_oldv, d_ord, d_tbits, d_kbits;
     size_t k1_row_cnt, k1_col_cnt, k1_col_ptr, k1_col_fill, k1_csc_row, k1_csc_val, k1_scale, k1_iso, k1_row_val;
     size_t k1_bad;
@@ -92,6 +93,7 @@ bool make_layout(const crwr_config& c, Layout& L) {
     else L.cand_cap = cap / 16 > 65536 ? cap / 16 : 65536;
     L.cand = bump(off, 8 * (size_t)(kCandHeader + L.cand_cap));
     L.merged = bump(off, 8 * (size_t)(c.n_shards > 1 ? (long long)c.n_shards * L.cand_cap : 1));
+    L.gathered = bump(off, 8 * (size_t)(c.n_shards > 1 ? (long long)c.n_shards * kPeerCandWords : 1));
     L.counts = bump(off, 4 * (size_t)(rows + 1));
     L.counts_scan = bump(off, 8 * (size_t)(rows + 1));
     L.total = bump(off, 8);
@@ -149,6 +151,10 @@ struct crwr_handle_s {
     WalkState* h_state = nullptr;               // pinned host mirror of the device state (polls)
     long long hint_len = -1, hint_kept = -1;    // last sizing hints (configure_shape is skipped when unchanged)
     long long hint_len_eff = 128;               // expected longest product row
+    PeerInfo peer = {nullptr, 0, 0};           // NVLink peer exchange (sharded walk), see peer.cuh
+    bool peer_attached = false;
+    unsigned long long* peer_block = nullptr;   // this rank's symmetric block
+    unsigned long long peer_epoch_base = 0;
     bool hist0_fused = false;                   // sharded step: level-0 histogram already filled by propagate
     bool profile = false;                       // CUDA events around every main propagate launch
     std::vector<cudaEvent_t> ev;                // start/end pairs
@@ -286,7 +292,10 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
 template <typename T>
 int launch_propagate(crwr_handle_s* h, int parity, bool fused, cudaStream_t st) {
     PropArgs<T> a = prop_args<T>(h, parity, fused);
-    if (!fused && h->cfg.n_shards > 1 && h->hist0_fused) a.hist = hist_ptr(h);   // sharded: histogram only, no scan tail
+    if (!fused && h->cfg.n_shards > 1 && h->hist0_fused) {
+        a.hist = hist_ptr(h);                       // sharded: histogram only, no scan tail
+        a.prefill_l1 = h->peer_attached ? 1 : 0;    // peer exchange: level 1 pre-filled for the predicted bin
+    }
     const int rows = a.n_rows;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
@@ -322,7 +331,17 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, cudaStream_t st) 
     return 0;
 }
 
-unsigned long long* hist_ptr(crwr_handle_s* h) { return h->at<unsigned long long>(h->L.xbuf) + kXExtras; }
+// Where this rank's step contributions go: its symmetric block when the peer exchange is attached (peers
+// read it over NVLink), else the local exchange buffer (which then also receives the all-reduced sums).
+unsigned long long* xbuf_ptr(crwr_handle_s* h) {
+    if (h->peer_attached) return h->peer_block + kPeerX;
+    return h->at<unsigned long long>(h->L.xbuf);
+}
+unsigned long long* hist_ptr(crwr_handle_s* h) { return xbuf_ptr(h) + kXExtras; }
+unsigned long long* cand_ptr(crwr_handle_s* h, int step) {
+    if (h->peer_attached) return h->peer_block + kPeerCand0 + (step & 1) * kPeerCandWords;
+    return h->at<unsigned long long>(h->L.cand);
+}
 
 template <typename T>
 int launch_hist(crwr_handle_s* h, int out_parity, int level, int fused, cudaStream_t st) {
@@ -360,7 +379,7 @@ template <typename T>
 int launch_gather(crwr_handle_s* h, int out_parity, int fused, cudaStream_t st) {
     const Layout& L = h->L;
     select_gather_kernel<T><<<h->sm_count, 512, 0, st>>>(h->at<T>(L.it_vals[out_parity]), h->at<WalkState>(L.state),
-                                                         h->at<unsigned long long>(L.cand), (unsigned long long)L.cand_cap,
+                                                         cand_ptr(h, h->steps_enqueued), (unsigned long long)L.cand_cap,
                                                          fused, finish_args(h, 1, nullptr));
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -832,8 +851,10 @@ int32_t crwr_step_propagate(crwr_handle h, void* stream) {
     h->hist0_fused = h->steps_enqueued >= 1;
     int e = f64 ? launch_propagate<double>(h, parity, false, st) : launch_propagate<float>(h, parity, false, st);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "propagate launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    pack_exchange_kernel<<<1, 32, 0, st>>>(h->at<WalkState>(h->L.state), h->at<unsigned long long>(h->L.xbuf));
-    LAUNCH_CHECK();
+    if (!h->peer_attached) {        // with the peer exchange the counters are published by crwr_step_peer_scan
+        pack_exchange_kernel<<<1, 32, 0, st>>>(h->at<WalkState>(h->L.state), xbuf_ptr(h));
+        LAUNCH_CHECK();
+    }
     return CRWR_OK;
 }
 int32_t crwr_step_hist(crwr_handle h, int32_t level, void* stream) {
@@ -868,6 +889,54 @@ int32_t crwr_step_finish(crwr_handle h, const void* d_gathered_blocks, void* str
     h->steps_enqueued += 1;
     return CRWR_OK;
 }
+// ---- NVLink peer exchange (sharded walk without NCCL in the step loop) ------------------------------------
+int64_t crwr_peer_block_bytes(void) { return 8 * (int64_t)kPeerWords; }
+
+int32_t crwr_peer_attach(crwr_handle h, void* d_block_ptrs, int32_t rank, uint64_t epoch_base) {
+    if (!h || !d_block_ptrs) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    if (h->cfg.n_shards < 2 || h->cfg.n_shards > kPeerFlags) CRWR_FAIL(CRWR_ERR_INVALID, "peer exchange needs 2..%d shards", kPeerFlags);
+    if (rank < 0 || rank >= h->cfg.n_shards) CRWR_FAIL(CRWR_ERR_INVALID, "rank out of range");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    unsigned long long* mine = nullptr;
+    CUDA_TRY(cudaMemcpy(&mine, (unsigned long long**)d_block_ptrs + rank, sizeof(mine), cudaMemcpyDeviceToHost));
+    h->peer.blocks = (unsigned long long* const*)d_block_ptrs;
+    h->peer.world = h->cfg.n_shards;
+    h->peer.rank = rank;
+    h->peer_block = mine;
+    h->peer_epoch_base = epoch_base;
+    h->peer_attached = true;
+    return CRWR_OK;
+}
+
+// Cross-GPU barrier + sum of the peers' counters / histogram bins + scan.  level -1: counters only (step 0).
+int32_t crwr_step_peer_scan(crwr_handle h, int32_t level, void* stream) {
+    STEP_PROLOGUE();
+    if (!h->peer_attached) CRWR_FAIL(CRWR_ERR_STATE, "crwr_peer_attach first");
+    if (level < -1 || level >= kSelectLevels) CRWR_FAIL(CRWR_ERR_INVALID, "level out of range");
+    const unsigned long long epoch = h->peer_epoch_base + 3ull * (unsigned long long)h->steps_enqueued + (level == 1 ? 2ull : 1ull);
+    unsigned long long* local = h->at<unsigned long long>(h->L.xbuf);
+    if (f64) peer_scan_kernel<double><<<1, 1024, 0, st>>>(h->at<WalkState>(h->L.state), h->peer, local, level, epoch);
+    else peer_scan_kernel<float><<<1, 1024, 0, st>>>(h->at<WalkState>(h->L.state), h->peer, local, level, epoch);
+    LAUNCH_CHECK();
+    return CRWR_OK;
+}
+
+int32_t crwr_step_peer_finish(crwr_handle h, void* stream) {
+    STEP_PROLOGUE();
+    if (!h->peer_attached) CRWR_FAIL(CRWR_ERR_STATE, "crwr_peer_attach first");
+    const int step = h->steps_enqueued;
+    const int do_select = step >= 1 ? 1 : 0;
+    const unsigned long long epoch = h->peer_epoch_base + 3ull * (unsigned long long)step + 3ull;
+    FinishArgs a = finish_args(h, do_select, nullptr);
+    a.xch = h->at<unsigned long long>(h->L.xbuf);         // local buffer: holds the sums peer_scan stored
+    unsigned long long* gathered = h->at<unsigned long long>(h->L.gathered);
+    if (f64) peer_finish_kernel<double><<<1, 1024, 0, st>>>(a, h->peer, gathered, step & 1, epoch);
+    else peer_finish_kernel<float><<<1, 1024, 0, st>>>(a, h->peer, gathered, step & 1, epoch);
+    LAUNCH_CHECK();
+    h->steps_enqueued += 1;
+    return CRWR_OK;
+}
+
 void* crwr_exchange_ptr(crwr_handle h, int32_t which) {
     if (!h) return nullptr;
     const Layout& L = h->L;
@@ -903,6 +972,7 @@ int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
     // the host-side step counter follows the device: steps enqueued past the stop were skipped
     if (s.done) h->steps_enqueued = s.step;
     if (s.debug_error) CRWR_FAIL(CRWR_ERR_STATE, "internal bounds check %d failed (CRWR_DEBUG_CHECKS build)", s.debug_error);
+    if (s.peer_timeout) CRWR_FAIL(CRWR_ERR_STATE, "a cross-GPU barrier timed out: a peer rank did not arrive");
     if (s.capacity_overflow) CRWR_FAIL(CRWR_ERR_CAPACITY, "iterate buffer overflow (capacity %lld entries)", (long long)h->cfg.iterate_cap);
     if (s.select_overflow) CRWR_FAIL(CRWR_ERR_CAPACITY, "percentile candidate buffer overflow");
     return CRWR_OK;

@@ -111,6 +111,8 @@ struct WalkState {
     int32_t hist1_ready;               // level-1 histogram already holds the counts of the selected level-0 bin
     unsigned int tick_dense, tick_hist1, tick_gather;   // last-CTA tickets
     unsigned int tick_prop;
+    int32_t peer_timeout;              // a cross-GPU barrier timed out (a peer rank is gone): the walk stops
+    int32_t pad5;
     int32_t debug_error;               // CRWR_DEBUG_CHECKS builds: highest failed bounds-check code (0 = none)
     int32_t pad4;
     unsigned long long phase_ns[8];    // persistent kernel: summed nanoseconds per phase (CTA 0's view), diagnostics

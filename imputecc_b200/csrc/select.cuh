@@ -343,7 +343,7 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
         st->parity ^= 1;
         st->step = step + 1;
         if (!done && step + 1 >= st->max_steps) { done = 1; reason = CRWR_STOP_MAX_STEPS; }
-        if (st->capacity_overflow || st->select_overflow) done = 1;
+        if (st->capacity_overflow || st->select_overflow || st->peer_timeout) done = 1;
         st->done = done;
         st->stop_reason = reason;
         st->last_fallback_rows = (int)fb;
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const T* vals, WalkSta
                                                           int level, int fused_tail) {
     __shared__ unsigned int sh[kSelectBins];
     if (st->done) return;
-    if (fused_tail && st->hist1_ready) return;      // the propagate epilogue already filled and scanned this level
+    if (level == 1 && st->hist1_ready) return;      // the propagate epilogue already filled this level and it was scanned
     hist_pass<T>(vals, (long long)st->cursor, (typename KeyOf<T>::type)st->prefix, level, sh, hist);
     if (fused_tail && last_block(&st->tick_hist1)) scan_level<T, 512>(st, hist, level);
 }

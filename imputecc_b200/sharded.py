@@ -15,6 +15,7 @@ in the CPU tests) on views of the library's workspace.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import scipy.sparse as sp
@@ -130,6 +131,86 @@ def run_sharded_walk(phases, comm, perc, max_steps):
         hints = comm.max_ints(phases.row_hints(st, perc, issued), phases.exchange(0))
 
 
+class PeerExchange:
+    """One symmetric-memory block per rank, mapped on every GPU of the group (NVLink peer access).
+
+    Created once per (process group, device) and reused by successive walks; ``next_epoch_base`` hands every
+    walk a fresh, strictly increasing range of barrier epochs so the flag words never need resetting."""
+
+    _cache = {}
+
+    def __init__(self, dist, group, device):
+        torch = _torch()
+        import torch.distributed._symmetric_memory as symm_mem
+        lib = _lib.load()
+        self.nbytes = int(lib.crwr_peer_block_bytes())
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.block = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.block.zero_()
+        self.handle = symm_mem.rendezvous(self.block, group)
+        offset = int(getattr(self.handle, "offset", 0))
+        ptrs = [int(p) + offset for p in self.handle.buffer_ptrs]
+        self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)      # device array of block pointers
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)                                              # every block is zeroed before any use
+        self.walks = 0
+
+    @classmethod
+    def get(cls, dist, group, device):
+        key = (id(group), str(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(dist, group, device)
+        return cls._cache[key]
+
+    def next_epoch_base(self) -> int:
+        self.walks += 1
+        return self.walks << 32
+
+    def attach(self, walker):
+        _lib.check(walker.lib.crwr_peer_attach(walker.handle, C.c_void_p(self.ptrs.data_ptr()), self.rank,
+                                               C.c_uint64(self.next_epoch_base())))
+
+
+def run_sharded_walk_peer(walker, perc, max_steps):
+    """The sharded walk with the exchanges fused into the consumer kernels (peer.cuh): no collective call in
+    the step loop, only kernel launches on this rank's stream.  The walker must be peer-attached."""
+    from .crwr import next_row_hints, poll_chunk
+    lib, h = walker.lib, walker.handle
+    issued = 0
+    hints = next_row_hints(0, 0, perc, 0)
+    while True:
+        chunk = min(poll_chunk(issued), max_steps - issued)
+        walker.set_row_hints(*hints)
+        for _ in range(chunk):
+            st = walker._stream()
+            _lib.check(lib.crwr_step_propagate(h, st))
+            if issued >= 1:
+                _lib.check(lib.crwr_step_peer_scan(h, 0, st))
+                _lib.check(lib.crwr_step_hist(h, 1, st))
+                _lib.check(lib.crwr_step_peer_scan(h, 1, st))
+                _lib.check(lib.crwr_step_gather(h, st))
+            else:
+                _lib.check(lib.crwr_step_peer_scan(h, -1, st))
+            _lib.check(lib.crwr_step_peer_finish(h, st))
+            issued += 1
+        status = walker.poll()
+        if status.stop_reason != 0 or issued >= max_steps:
+            return status
+        hints = walker.row_hints(status, perc, issued)      # local statistics: sizing affects speed only
+
+
+def peer_exchange_available(dist, group) -> bool:
+    """NVLink peer exchange needs NCCL ranks on one node and torch symmetric memory."""
+    if os.environ.get("CRWR_SHARDED_EXCHANGE", "peer") != "peer":
+        return False
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401
+    except Exception:
+        return False
+    return dist.get_backend(group) == "nccl" and 2 <= dist.get_world_size(group) <= 16
+
+
 def gather_row_blocks(dist, group, ip, ix, dt, rows_of_rank, m):
     """All-gather per-rank CSR row blocks (device tensors) into one m x m CSR on every rank."""
     torch = _torch()
@@ -191,8 +272,14 @@ def crwr_impute_sharded(normcc, marker_idx_sorted, rp, perc, tol=DEFAULT_TOL, ma
     try:
         nnz_p = w.build_transition(M.indptr, M.indices, M.data, new_of_old)
         with torch.cuda.device(device):
+            use_peer = peer_exchange_available(dist, group)
+            if use_peer:
+                PeerExchange.get(dist, group, device).attach(w)
             w.walk_init(rp, perc, tol, max_steps)
-            st = run_sharded_walk(CudaPhases(w), TorchComm(dist, group), perc, max_steps)
+            if use_peer:
+                st = run_sharded_walk_peer(w, perc, max_steps)
+            else:
+                st = run_sharded_walk(CudaPhases(w), TorchComm(dist, group), perc, max_steps)
             ip, ix, dt = w.result_device()
             f_ip, f_ix, f_dt = gather_row_blocks(dist, group, ip, ix, dt, ranges, m)
             e_ip, e_ix, e_dt = symmetrise_device(f_ip, f_ix, f_dt, m)

@@ -156,6 +156,21 @@ int32_t crwr_step_finish(crwr_handle h, const void* d_gathered_blocks, void* str
 void* crwr_exchange_ptr(crwr_handle h, int32_t which);     /* device pointer inside the workspace */
 int64_t crwr_exchange_bytes(crwr_handle h, int32_t which);
 
+/* Sharded walk over NVLink peer memory (no collective library in the step loop).  Every rank allocates one
+ * block of crwr_peer_block_bytes() in memory that all GPUs of the group have mapped (torch symmetric memory /
+ * CUDA IPC), zeroes it once, and attaches the device array of the n_shards block pointers (rank order).
+ * epoch_base must be the same on every rank and larger for every new walk on the same blocks (e.g. walk
+ * number << 32).  A step is then
+ *   crwr_step_propagate; crwr_step_peer_scan(0); crwr_step_hist(1); crwr_step_peer_scan(1);
+ *   crwr_step_gather; crwr_step_peer_finish                 (step 0: propagate; peer_scan(-1); peer_finish)
+ * peer_scan = cross-GPU flag barrier + sum of the peers' counters / histogram bins read over NVLink + scan;
+ * peer_finish = barrier + copy of the peers' candidate blocks + finish.  Results are bit-identical to the
+ * collective-based sequence and to the unsharded walk. */
+int64_t crwr_peer_block_bytes(void);
+int32_t crwr_peer_attach(crwr_handle h, void* d_block_ptrs, int32_t rank, uint64_t epoch_base);
+int32_t crwr_step_peer_scan(crwr_handle h, int32_t level, void* stream);
+int32_t crwr_step_peer_finish(crwr_handle h, void* stream);
+
 /* Synchronises the stream and fills *h_out. */
 int32_t crwr_walk_poll(crwr_handle h, crwr_status* h_out, void* stream);
 /* Copies the per-step records (steps_done of them, at most cap) to host; syncs. */
