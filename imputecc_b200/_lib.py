@@ -58,6 +58,7 @@ _SIGNATURES = {
     "crwr_set_mode": (C.c_int32, [_P, C.c_int32]),
     "crwr_phase_ns": (C.c_int32, [_P, C.POINTER(C.c_uint64), _P]),
     "crwr_get_shape": (C.c_int32, [_P, C.POINTER(C.c_int64)]),
+    "crwr_get_group_shape": (C.c_int32, [_P, C.POINTER(C.c_int64)]),
     "crwr_profile": (C.c_int32, [_P, C.c_int32]),
     "crwr_profile_phases": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "crwr_profile_read": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _P]),

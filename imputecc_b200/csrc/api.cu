@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "select.cuh"
 #include "propagate.cuh"
+#include "propagate_group.cuh"
 #include "transition.cuh"
 #include "finish.cuh"
 #include "walk.cuh"
@@ -136,8 +137,11 @@ struct crwr_handle_s {
     bool have_p;
     bool walking;
     int steps_enqueued;
-    PropShape shape;                // run-time sizing of the main propagate kernel
+    PropShape shape;                // run-time sizing of the warp-per-row propagate kernel (persistent mode)
     int grid;                       // its persistent grid size
+    GroupShape gshape;              // run-time sizing of the row-group propagate kernel (default)
+    int ggrid = 0;                  // its persistent grid size
+    int prop_kind = 1;              // 1: row-group kernel (default), 0: warp-per-row kernel (CRWR_PROP=warp)
     // 0 (default): one launch per phase.  1: one cooperative kernel per chunk of steps - measured equal for
     // float32 small-row workloads and 10-15 % slower for float64 (small CTAs make CTA 0's serial scan/finish
     // phases slower), so it is opt-in.
@@ -249,6 +253,92 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
     return 0;
 }
 
+template <typename T, int G>
+int group_kernel_attr(size_t smem, int threads, int* per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(propagate_group_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, propagate_group_kernel<T, G>, threads, smem);
+    return (int)e;
+}
+
+// Sizes the row-group kernel: table / kept list per row from the caller's hints, lanes per row from the mean
+// P row length (one P row per round) and from the number of rows that fit an SM.
+template <typename T>
+int configure_group_shape(crwr_handle_s* h, long long max_row_len, long long max_kept) {
+    const long long n = h->cfg.n_contigs;
+    const long long rows = h->cfg.row_end - h->cfg.row_begin;
+    long long want = max_row_len + max_row_len / 3 + 32;          // distinct output columns to provide for (rows still grow
+                                                                  // by a quarter between the last early poll and the plateau)
+    if (want < 48) want = 48;
+    if (want > n + 16) want = n + 16;
+    long long kmax = round_up(max_kept + max_kept / 8 + 8, 16);
+    if (kmax < 32) kmax = 32;
+    if (kmax > n) kmax = round_up(n, 16);
+    const size_t win_bytes = kHistWin * sizeof(unsigned int);
+    const size_t budget = (size_t)h->max_smem_optin - win_bytes;
+    // lanes per row: about one P row per round (CRWR_GROUP overrides)
+    const double avg_deg = h->p_nnz > 0 ? (double)h->p_nnz / (double)n : 8.0;
+    int G = avg_deg <= 6.0 ? 8 : (avg_deg <= 20.0 ? 16 : 32);
+    if (const char* e = getenv("CRWR_GROUP")) { const int g = atoi(e); if (g == 4 || g == 8 || g == 16 || g == 32) G = g; }
+    int wmax = 4;
+    if (const char* e = getenv("CRWR_GROUP_WARPS")) { const int g = atoi(e); if (g >= 1 && g <= 8) wmax = g; }
+    // two-slot buckets want a load below ~0.55 at the longest row; a tighter table (up to 0.7) is accepted when it
+    // lets every row of the shard be in flight at once (one wave: the step is then as long as its slowest row)
+    auto make = [&](int load_pct, long long* in_flight) -> GroupShape {
+        GroupShape sh;
+        long long w_ = want, km = kmax;
+        for (;;) {
+            long long H = round_up(w_ * 100 / load_pct + 2, 16);
+            if (H > 65520) { H = 65520; w_ = H * load_pct / 100; }
+            if (km > H) km = H;
+            sh.H = (int)H; sh.limit = (int)round_up(w_, 8); sh.kmax = (int)km;
+            sh.ov_cap = (int)(w_ / 8 < 16 ? 16 : (w_ / 8 > 256 ? 256 : round_up(w_ / 8, 8)));
+            sh.per_row = group_smem_per_row<T>(sh.H, sh.limit, sh.kmax, sh.ov_cap);
+            if (sh.per_row <= budget) break;
+            // too big for one SM: shrink (oversized rows are deferred to the large-row kernel)
+            if (km > 1024 && km * 2 > w_) km = round_up(km / 2, 16);
+            else w_ = w_ * 3 / 4;
+        }
+        int g = G;
+        while (g < 32 && (size_t)(32 / g) * sh.per_row > budget) g *= 2;
+        int w = (int)(budget / ((size_t)(32 / g) * sh.per_row));
+        if (w > wmax) w = wmax;
+        if (w < 1) w = 1;
+        sh.G = g;
+        sh.warps = w;
+        const size_t smem = sh.per_row * (size_t)w * (32 / g) + win_bytes;
+        const long long per_sm = (long long)(((size_t)h->max_smem_optin + 1024) / (smem + 1024));   // 1 KB reserved per CTA
+        *in_flight = per_sm * h->sm_count * w * (32 / g);
+        return sh;
+    };
+    long long fl = 0;
+    GroupShape best = make(55, &fl);
+    if (fl < rows) {
+        const int loads[2] = {62, 70};
+        for (int li = 0; li < 2; ++li) {
+            GroupShape cand = make(loads[li], &fl);
+            if (fl >= rows) { best = cand; break; }
+        }
+    }
+    GroupShape sh = best;
+    sh.rank_sort_max = 128;
+    if (const char* e = getenv("CRWR_RANK_SORT_MAX")) sh.rank_sort_max = atoi(e);
+    const int g = sh.G, w = sh.warps;
+    const size_t smem = sh.per_row * (size_t)w * (32 / g) + win_bytes;
+    int per_sm = 0, e = 0;
+    switch (g) {
+        case 4: e = group_kernel_attr<T, 4>(smem, w * 32, &per_sm); break;
+        case 8: e = group_kernel_attr<T, 8>(smem, w * 32, &per_sm); break;
+        case 16: e = group_kernel_attr<T, 16>(smem, w * 32, &per_sm); break;
+        default: e = group_kernel_attr<T, 32>(smem, w * 32, &per_sm); break;
+    }
+    if (e) return e;
+    if (per_sm < 1) per_sm = 1;
+    h->gshape = sh;
+    h->ggrid = per_sm * h->sm_count;
+    return 0;
+}
+
 unsigned long long* hist_ptr(crwr_handle_s* h);
 
 template <typename T>
@@ -302,7 +392,20 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, cudaStream_t st) 
         if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
         cudaEventRecord(e0, st);
     }
-    {
+    if (h->prop_kind == 1 && h->steps_enqueued >= 1) {      // step 0 keeps scipy's storage order (warp-per-row kernel)
+        const GroupShape& sh = h->gshape;
+        const int rpc = sh.warps * (32 / sh.G);          // rows per CTA and pass
+        int grid = (rows + rpc - 1) / rpc;
+        if (grid > h->ggrid) grid = h->ggrid;
+        if (grid < 1) grid = 1;
+        const size_t smem = sh.per_row * (size_t)rpc + kHistWin * sizeof(unsigned int);
+        switch (sh.G) {
+            case 4: propagate_group_kernel<T, 4><<<grid, sh.warps * 32, smem, st>>>(a, sh); break;
+            case 8: propagate_group_kernel<T, 8><<<grid, sh.warps * 32, smem, st>>>(a, sh); break;
+            case 16: propagate_group_kernel<T, 16><<<grid, sh.warps * 32, smem, st>>>(a, sh); break;
+            default: propagate_group_kernel<T, 32><<<grid, sh.warps * 32, smem, st>>>(a, sh); break;
+        }
+    } else {
         const PropShape& sh = h->shape;
         int grid = (rows + sh.warps - 1) / sh.warps;
         if (grid > h->grid) grid = h->grid;
@@ -602,10 +705,12 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
         CRWR_FAIL(CRWR_ERR_CUDA, "workspace memset failed");
     }
     int e = cfg->dtype == CRWR_F64 ? configure_shape<double>(h, 192, 32) : configure_shape<float>(h, 192, 32);
+    if (!e) e = cfg->dtype == CRWR_F64 ? configure_group_shape<double>(h, 192, 32) : configure_group_shape<float>(h, 192, 32);
     if (e) {
         delete h;
         CRWR_FAIL(CRWR_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
     }
+    if (const char* k = getenv("CRWR_PROP")) h->prop_kind = strcmp(k, "warp") == 0 ? 0 : 1;
     *out = h;
     return CRWR_OK;
 }
@@ -787,6 +892,9 @@ int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept)
     int e = h->cfg.dtype == CRWR_F64 ? configure_shape<double>(h, max_row_len, max_kept)
                                      : configure_shape<float>(h, max_row_len, max_kept);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "kernel sizing failed: %s", cudaGetErrorString((cudaError_t)e));
+    e = h->cfg.dtype == CRWR_F64 ? configure_group_shape<double>(h, max_row_len, max_kept)
+                                 : configure_group_shape<float>(h, max_row_len, max_kept);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "row-group kernel sizing failed: %s", cudaGetErrorString((cudaError_t)e));
     h->hint_len = max_row_len;
     h->hint_kept = max_kept;
     h->hint_len_eff = max_row_len;
@@ -812,6 +920,14 @@ int32_t crwr_get_shape(crwr_handle h, int64_t* h_out8) {
     if (!h || !h_out8) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
     h_out8[0] = h->shape.H; h_out8[1] = h->shape.limit; h_out8[2] = h->shape.kmax; h_out8[3] = h->shape.scap;
     h_out8[4] = h->shape.warps; h_out8[5] = (int64_t)h->shape.per_warp; h_out8[6] = h->grid; h_out8[7] = h->sm_count;
+    return CRWR_OK;
+}
+
+int32_t crwr_get_group_shape(crwr_handle h, int64_t* h_out8) {
+    if (!h || !h_out8) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    const GroupShape& g = h->gshape;
+    h_out8[0] = g.H; h_out8[1] = g.limit; h_out8[2] = g.kmax; h_out8[3] = g.ov_cap;
+    h_out8[4] = g.G; h_out8[5] = g.warps; h_out8[6] = (int64_t)g.per_row; h_out8[7] = h->prop_kind == 1 ? h->ggrid : 0;
     return CRWR_OK;
 }
 
@@ -975,6 +1091,7 @@ int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
     if (s.peer_timeout) CRWR_FAIL(CRWR_ERR_STATE, "a cross-GPU barrier timed out: a peer rank did not arrive");
     if (s.capacity_overflow) CRWR_FAIL(CRWR_ERR_CAPACITY, "iterate buffer overflow (capacity %lld entries)", (long long)h->cfg.iterate_cap);
     if (s.select_overflow) CRWR_FAIL(CRWR_ERR_CAPACITY, "percentile candidate buffer overflow");
+    if (s.order_hazard) CRWR_FAIL(CRWR_ERR_STATE, "a walk step ended without a percentile cut although its rows were stored unordered (set CRWR_PROP=warp)");
     return CRWR_OK;
 }
 

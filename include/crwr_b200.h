@@ -130,6 +130,9 @@ int64_t crwr_transition_nnz(crwr_handle h);
 int32_t crwr_phase_ns(crwr_handle h, uint64_t* h_out8, void* stream);
 /* Current kernel sizing (diagnostics): {H, limit, kmax, scap, warps/CTA, smem bytes/warp, grid, SMs}. */
 int32_t crwr_get_shape(crwr_handle h, int64_t* h_out8);
+/* Sizing of the row-group propagate kernel (steps >= 1; diagnostics):
+ * {table slots/row, max columns/row, max kept/row, overflow entries/row, lanes/row, warps/CTA, smem bytes/row, grid}. */
+int32_t crwr_get_group_shape(crwr_handle h, int64_t* h_out8);
 
 /* Execution mode of crwr_walk_enqueue: 0 (default) launches one kernel per phase of a step (always used by the
  * sharded walk); 1 runs a chunk of steps as ONE persistent cooperative kernel with grid barriers between the

