@@ -7,6 +7,7 @@
 #include <vector>
 #include <mutex>
 #include <cmath>
+#include <utility>
 
 #include "common.cuh"
 #include "select.cuh"
@@ -46,6 +47,22 @@ static long long g_launches = 0;
 namespace {
 
 constexpr int kDenseWarpsPerCta = 4;
+
+// Launch with programmatic stream serialization (see pdl_wait in common.cuh) when `pdl`, else the ordinary way.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 struct Layout {
     size_t state, trace, p_indptr, p_cols, p_vals;
@@ -142,6 +159,7 @@ struct crwr_handle_s {
     GroupShape gshape;              // run-time sizing of the row-group propagate kernel (default)
     int ggrid = 0;                  // its persistent grid size
     int prop_kind = 1;              // 1: row-group kernel (default), 0: warp-per-row kernel (CRWR_PROP=warp)
+    int pdl_forced = -1;            // CRWR_PDL=0/1: programmatic dependent launch forced off/on (-1: by row length, use_pdl)
     // 0 (default): one launch per phase.  1: one cooperative kernel per chunk of steps - measured equal for
     // float32 small-row workloads and 10-15 % slower for float64 (small CTAs make CTA 0's serial scan/finish
     // phases slower), so it is opt-in.
@@ -271,7 +289,7 @@ int configure_group_shape(crwr_handle_s* h, long long max_row_len, long long max
                                                                   // by a quarter between the last early poll and the plateau)
     if (want < 48) want = 48;
     if (want > n + 16) want = n + 16;
-    long long kmax = round_up(max_kept + max_kept / 8 + 8, 16);
+    long long kmax = round_up(max_kept + max_kept * 3 / 10 + 8, 16);
     if (kmax < 32) kmax = 32;
     if (kmax > n) kmax = round_up(n, 16);
     const size_t win_bytes = kHistWin * sizeof(unsigned int);
@@ -341,6 +359,16 @@ int configure_group_shape(crwr_handle_s* h, long long max_row_len, long long max
 
 unsigned long long* hist_ptr(crwr_handle_s* h);
 
+// Programmatic dependent launch of the step kernels (common.cuh, pdl_wait): hides the launch gaps between the four
+// dependent kernels of a step.  Measured on B200: -9 % per step at ~100-entry rows (90 -> 81 us), +4 % at ~650-entry
+// rows (673 -> 700 us; CTAs parked in pdl_wait share the SMs with long-running predecessors), so it is used for
+// short rows only.  CRWR_PDL=0/1 forces it off/on.
+bool use_pdl(const crwr_handle_s* h) {
+    if (h->cfg.n_shards != 1) return false;
+    if (h->pdl_forced >= 0) return h->pdl_forced != 0;
+    return h->hint_len_eff <= 384;
+}
+
 template <typename T>
 PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     const Layout& L = h->L;
@@ -363,6 +391,7 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     a.hist = fused ? hist_ptr(h) : nullptr;
     a.fused_select = fused ? 1 : 0;
     a.prefill_l1 = fused ? 1 : 0;
+    a.part = nullptr;                           // lumped level-0 window: not enabled
     // a warp reserves output space for a few rows at a time (zero-padded leftovers are skipped by the select)
     {
         long long ch = 3 * (long long)h->hint_len_eff;
@@ -387,6 +416,7 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, cudaStream_t st) 
         a.prefill_l1 = h->peer_attached ? 1 : 0;    // peer exchange: level 1 pre-filled for the predicted bin
     }
     const int rows = a.n_rows;
+    const bool pdl = use_pdl(h);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
         if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
@@ -400,17 +430,17 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, cudaStream_t st) 
         if (grid < 1) grid = 1;
         const size_t smem = sh.per_row * (size_t)rpc + kHistWin * sizeof(unsigned int);
         switch (sh.G) {
-            case 4: propagate_group_kernel<T, 4><<<grid, sh.warps * 32, smem, st>>>(a, sh); break;
-            case 8: propagate_group_kernel<T, 8><<<grid, sh.warps * 32, smem, st>>>(a, sh); break;
-            case 16: propagate_group_kernel<T, 16><<<grid, sh.warps * 32, smem, st>>>(a, sh); break;
-            default: propagate_group_kernel<T, 32><<<grid, sh.warps * 32, smem, st>>>(a, sh); break;
+            case 4: launch_k(pdl, propagate_group_kernel<T, 4>, grid, sh.warps * 32, smem, st, a, sh); break;
+            case 8: launch_k(pdl, propagate_group_kernel<T, 8>, grid, sh.warps * 32, smem, st, a, sh); break;
+            case 16: launch_k(pdl, propagate_group_kernel<T, 16>, grid, sh.warps * 32, smem, st, a, sh); break;
+            default: launch_k(pdl, propagate_group_kernel<T, 32>, grid, sh.warps * 32, smem, st, a, sh); break;
         }
     } else {
         const PropShape& sh = h->shape;
         int grid = (rows + sh.warps - 1) / sh.warps;
         if (grid > h->grid) grid = h->grid;
         if (grid < 1) grid = 1;
-        propagate_kernel<T><<<grid, sh.warps * 32, sh.per_warp * (size_t)sh.warps + kHistWin * sizeof(unsigned int), st>>>(a, sh);
+        launch_k(pdl, propagate_kernel<T>, grid, sh.warps * 32, sh.per_warp * (size_t)sh.warps + kHistWin * sizeof(unsigned int), st, a, sh);
     }
     ++g_launches;
     if (h->profile) {
@@ -428,7 +458,7 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, cudaStream_t st) 
     sc.kbits = h->at<uint32_t>(L.d_kbits);
     sc.n = h->cfg.n_contigs;
     sc.words = L.words;
-    propagate_dense_kernel<T, kDenseWarpsPerCta><<<(int)(L.dense_warps / kDenseWarpsPerCta), kDenseWarpsPerCta * 32, 0, st>>>(a, sc);
+    launch_k(pdl, propagate_dense_kernel<T, kDenseWarpsPerCta>, (int)(L.dense_warps / kDenseWarpsPerCta), kDenseWarpsPerCta * 32, 0, st, a, sc);
     ++g_launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
     return 0;
@@ -449,8 +479,8 @@ unsigned long long* cand_ptr(crwr_handle_s* h, int step) {
 template <typename T>
 int launch_hist(crwr_handle_s* h, int out_parity, int level, int fused, cudaStream_t st) {
     const Layout& L = h->L;
-    select_hist_kernel<T><<<h->sm_count, 512, 0, st>>>(h->at<T>(L.it_vals[out_parity]), h->at<WalkState>(L.state),
-                                                       hist_ptr(h), level, fused);
+    launch_k(use_pdl(h), select_hist_kernel<T>, h->sm_count, 512, 0, st, (const T*)h->at<T>(L.it_vals[out_parity]),
+             h->at<WalkState>(L.state), hist_ptr(h), level, fused);
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -475,22 +505,23 @@ FinishArgs finish_args(crwr_handle_s* h, int do_select, const void* gathered) {
     a.cand_cap = (unsigned long long)L.cand_cap;
     a.trace = h->at<crwr_step_record>(L.trace);
     a.do_select = do_select;
+    a.part = nullptr;
     return a;
 }
 
 template <typename T>
 int launch_gather(crwr_handle_s* h, int out_parity, int fused, cudaStream_t st) {
     const Layout& L = h->L;
-    select_gather_kernel<T><<<h->sm_count, 512, 0, st>>>(h->at<T>(L.it_vals[out_parity]), h->at<WalkState>(L.state),
-                                                         cand_ptr(h, h->steps_enqueued), (unsigned long long)L.cand_cap,
-                                                         fused, finish_args(h, 1, nullptr));
+    launch_k(use_pdl(h), select_gather_kernel<T>, h->sm_count, 512, 0, st, (const T*)h->at<T>(L.it_vals[out_parity]),
+             h->at<WalkState>(L.state), cand_ptr(h, h->steps_enqueued), (unsigned long long)L.cand_cap, fused,
+             finish_args(h, 1, nullptr));
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 // gathered: candidate blocks of all ranks (sharded) or null (own block only)
 template <typename T>
 int launch_finish(crwr_handle_s* h, int do_select, const void* gathered, cudaStream_t st) {
-    finish_step_kernel<T><<<1, 1024, 0, st>>>(finish_args(h, do_select, gathered));
+    launch_k(use_pdl(h), finish_step_kernel<T>, 1, 1024, 0, st, finish_args(h, do_select, gathered));
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -711,6 +742,7 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
         CRWR_FAIL(CRWR_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
     }
     if (const char* k = getenv("CRWR_PROP")) h->prop_kind = strcmp(k, "warp") == 0 ? 0 : 1;
+    if (const char* k = getenv("CRWR_PDL")) h->pdl_forced = atoi(k) != 0 ? 1 : 0;
     *out = h;
     return CRWR_OK;
 }

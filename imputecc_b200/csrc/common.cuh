@@ -149,9 +149,51 @@ constexpr int kCandHeader = 2;
 // records the highest failed check code in the walk state instead of trapping; crwr_walk_poll reports it.
 #ifdef CRWR_DEBUG_CHECKS
 #define CRWR_CHECK(st, cond, code) do { if (!(cond)) atomicMax(&(st)->debug_error, (int)(code)); } while (0)
+// loop guard: after `limit` iterations the code is recorded and `action` leaves the loop
+#define CRWR_GUARD_DECL(g) int g = 0
+#define CRWR_GUARD(st, g, limit, code, action) do { if (++(g) > (limit)) { atomicMax(&(st)->debug_error, (int)(code)); action; } } while (0)
 #else
+#define CRWR_GUARD_DECL(g) do { } while (0)
+#define CRWR_GUARD(st, g, limit, code, action) do { } while (0)
 #define CRWR_CHECK(st, cond, code) do { } while (0)
 #endif
+
+// ---------------------------------------------------------------------------------------------
+// Exact, partition-independent sums of squares (||Q - Q~||_F^2, utility.py:283): every term is converted
+// to 2^-64 fixed point on its own (integer part and fraction kept apart), so the integer sums do not
+// depend on which lanes, warps, kernels or GPUs added them.
+// ---------------------------------------------------------------------------------------------
+struct Sq128 { unsigned long long lo, hi; };
+__device__ __forceinline__ void sq_add(Sq128& a, double x) {      // x >= 0
+    if (!(x > 0.0)) return;
+    if (x >= 9.0e18) x = 9.0e18;
+    const double h = floor(x);
+    const unsigned long long f = __double2ull_rd((x - h) * 18446744073709551616.0);
+    a.hi += __double2ull_rd(h);
+    a.lo += f;
+    a.hi += (a.lo < f) ? 1ull : 0ull;
+}
+__device__ __forceinline__ void sq_merge(Sq128& a, unsigned long long lo, unsigned long long hi) {
+    a.lo += lo;
+    a.hi += hi + ((a.lo < lo) ? 1ull : 0ull);
+}
+// Sum over the lanes of an aligned group of `width` lanes (all lanes of the warp take part).
+__device__ __forceinline__ Sq128 sq_group_sum(Sq128 s, int width) {
+    for (int o = width >> 1; o > 0; o >>= 1) {
+        const unsigned long long olo = __shfl_xor_sync(kFull, s.lo, o);
+        const unsigned long long ohi = __shfl_xor_sync(kFull, s.hi, o);
+        sq_merge(s, olo, ohi);
+    }
+    return s;
+}
+// pos - neg, where neg's terms are a subset of pos's (so the difference is a sum of squares again)
+__device__ __forceinline__ Sq128 sq_diff(const Sq128& pos, const Sq128& neg) {
+    Sq128 r;
+    r.lo = pos.lo - neg.lo;
+    r.hi = pos.hi - neg.hi - ((pos.lo < neg.lo) ? 1ull : 0ull);
+    return r;
+}
+
 
 template <typename T>
 struct IterBuf {
@@ -160,6 +202,16 @@ struct IterBuf {
     long long* row_ptr;
     int32_t* row_len;
 };
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): the kernels of a walk step are launched with programmatic stream
+// serialization, so the CTAs of kernel N+1 are brought onto the SMs while kernel N drains and only wait here
+// until N has completed and its writes are visible - the launch gap between the dependent kernels of a step
+// disappears.  Both are no-ops for a kernel launched the ordinary way.  Rule: every kernel of the chain waits
+// before it reads anything another kernel wrote and before it exits (completion is transitive only then).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // Warp helpers

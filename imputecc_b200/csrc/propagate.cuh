@@ -83,16 +83,10 @@ __device__ __forceinline__ void totals_init(WarpTotals& w) {
 
 // Integer limbs commute, so delta is bit-identical whatever the order in which rows finish and however
 // the rows are sharded over GPUs.
-__device__ __forceinline__ void totals_add_rowsq(WarpTotals& w, double x) {
-    if (!(x > 0.0)) return;
-    if (x >= 4294967296.0) x = 4294967295.0;
-    const double hi = floor(x);
-    const double f1 = (x - hi) * 4294967296.0;
-    const double m1 = floor(f1);
-    const double m0 = floor((f1 - m1) * 4294967296.0);
-    w.sq2 += (unsigned long long)hi;
-    w.sq1 += (unsigned long long)m1;
-    w.sq0 += (unsigned long long)m0;
+__device__ __forceinline__ void totals_add_rowsq(WarpTotals& w, const Sq128& r) {
+    w.sq2 += r.hi;
+    w.sq1 += r.lo >> 32;
+    w.sq0 += r.lo & 0xffffffffull;
 }
 
 template <typename T>
@@ -591,7 +585,7 @@ __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropS
         const bool diag_new = dslot < 0;
         const int n_cand = count + (diag_new ? 1 : 0);
         const long long base = reserve_row(a, wt, n_cand);
-        double s1 = 0.0;
+        Sq128 pos = {0ull, 0ull}, neg = {0ull, 0ull};
         int nz = 0;
         for (int b = 0; b < count; b += 32) {
             const int i = b + lane;
@@ -602,19 +596,18 @@ __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropS
                 v = mul_rn(a.scale, tval[slot]);
                 if (slot == dslot) v = add_rn(v, a.restart);
                 tval[slot] = v;
-                s1 += (double)v * (double)v;
+                sq_add(pos, (double)v * (double)v);
                 one = v != (T)0;
             }
             nz += __popc(__ballot_sync(kFull, one));
             if (a.hist) hist_values<T>(a.hist, win, one, v, pred_valid, pred0);
         }
         if (diag_new) {
-            if (lane == 0) s1 += (double)a.restart * (double)a.restart;
+            if (lane == 0) sq_add(pos, (double)a.restart * (double)a.restart);
             if (a.restart != (T)0) nz += 1;
             if (a.hist) hist_values<T>(a.hist, win, lane == 0 && a.restart != (T)0, a.restart, pred_valid, pred0);
         }
         __syncwarp();
-        double s2 = 0.0;
         for (int idx = lane; idx < nk; idx += 32) {
             const int32_t j = kcol[idx];
             const T oldv = kval[idx];
@@ -633,9 +626,10 @@ __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropS
             if (found) newv = tval[slot];
             else if (j == dcol) newv = a.restart;
             const T d = sub_rn(oldv, newv);
-            s2 += (double)d * (double)d - (double)newv * (double)newv;
+            sq_add(pos, (double)d * (double)d);
+            sq_add(neg, (double)newv * (double)newv);
         }
-        totals_add_rowsq(wt, warp_sum(s1 + s2));
+        totals_add_rowsq(wt, sq_diff(sq_group_sum(pos, 32), sq_group_sum(neg, 32)));
 
         const int shift = diag_new ? 1 : 0;
         write_row(a, wt, row, base, n_cand, nz, [&](int i, int32_t& c, T& v) {
@@ -654,8 +648,10 @@ __device__ __forceinline__ void propagate_rows(const PropArgs<T>& a, const PropS
 template <typename T>
 __global__ void __launch_bounds__(256) propagate_kernel(PropArgs<T> a, PropShape sh) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_wait();
     if (a.st->done) return;
     propagate_rows<T, false>(a, sh, smem_raw);
+    pdl_launch_dependents();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -780,7 +776,7 @@ __device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScra
 
         const int32_t dcol = a.row_begin + row;
         const bool diag_new = ((tbits[dcol >> 5] >> (dcol & 31)) & 1u) == 0u;
-        double s1 = 0.0;
+        Sq128 pos = {0ull, 0ull}, neg = {0ull, 0ull};
         int nz = 0;
         for (int b = 0; b < count; b += 32) {
             int i = b + lane;
@@ -791,7 +787,7 @@ __device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScra
                 v = mul_rn(a.scale, acc[j]);
                 if (j == dcol) v = add_rn(v, a.restart);
                 acc[j] = v;
-                s1 += (double)v * (double)v;
+                sq_add(pos, (double)v * (double)v);
                 one = v != (T)0;
             }
             nz += __popc(__ballot_sync(kFull, one));
@@ -799,14 +795,13 @@ __device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScra
             else if (a.hist) hist_values<T>(a.hist, win, one, v, pred_valid, pred0);
         }
         if (diag_new) {
-            if (lane == 0) s1 += (double)a.restart * (double)a.restart;
+            if (lane == 0) sq_add(pos, (double)a.restart * (double)a.restart);
             if (a.restart != (T)0) nz += 1;
             if (rep) hist_lumped_global<T>(rep, a.hist, win_lo, win_valid, lane == 0 && a.restart != (T)0, a.restart, pred_valid, pred0);
             else if (a.hist) hist_values<T>(a.hist, win, lane == 0 && a.restart != (T)0, a.restart, pred_valid, pred0);
         }
         __syncwarp();
         // old entries: every kept column has its bit in kbits and its value in oldv
-        double s2 = 0.0;
         for (int b = 0; b < len; b += 32) {
             int e = b + lane;
             if (e < len) {
@@ -817,11 +812,12 @@ __device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScra
                     if ((tbits[j >> 5] >> (j & 31)) & 1u) newv = acc[j];
                     else if (j == dcol) newv = a.restart;
                     const T d = sub_rn(o, newv);
-                    s2 += (double)d * (double)d - (double)newv * (double)newv;
+                    sq_add(pos, (double)d * (double)d);
+            sq_add(neg, (double)newv * (double)newv);
                 }
             }
         }
-        totals_add_rowsq(wt, warp_sum(s1 + s2));
+        totals_add_rowsq(wt, sq_diff(sq_group_sum(pos, 32), sq_group_sum(neg, 32)));
 
         const int n_cand = count + (diag_new ? 1 : 0);
         const int shift = diag_new ? 1 : 0;
@@ -842,7 +838,11 @@ __device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScra
 template <typename T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T> a, DenseScratch<T> sc) {
     __shared__ unsigned int win[kHistWin];
+    pdl_wait();
     if (a.st->done) return;
+    // deferred rows can take long: the next kernel's CTAs are let in early only when there are none (CTAs waiting
+    // in pdl_wait on the same SMs were measured to slow the rows down)
+    if (a.st->fb_count == 0) pdl_launch_dependents();
     if (a.st->fb_count == 0) {
         // the usual case: no row was deferred, the step's histogram is already complete.  No CTA has row
         // work, so no "last CTA" is needed: CTA 0 scans, the others leave at once.

@@ -81,7 +81,6 @@ __device__ __forceinline__ void group_sort_pairs(int32_t* key, T* val, int n, in
 template <typename T, int G>
 __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, GroupShape sh) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (a.st->done) return;
     constexpr int RPW = 32 / G;                      // rows per warp
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
@@ -124,6 +123,8 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
     unsigned int* win = reinterpret_cast<unsigned int*>(smem_raw + (size_t)sh.warps * RPW * sh.per_row);
     for (int i = threadIdx.x; i < kHistWin; i += blockDim.x) win[i] = 0u;
     for (int i = sub; i < H; i += G) tkey[i] = -1;
+    pdl_wait();                                      // the tables above are set up while the previous kernel drains
+    if (a.st->done) return;
     __syncthreads();
 
     if (blockIdx.x == 0 && threadIdx.x == 0) a.st->unordered_rows = 1;
@@ -138,6 +139,9 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
     unsigned long long t_sq0 = 0, t_sq1 = 0, t_sq2 = 0, t_nnz = 0, t_kept = 0;
     int t_max_kept = 0, t_max_len = 0;
 
+    // Rows are handed out by an atomic counter.  (Measured and rejected: a static first pass - 9 % slower on long
+    // rows, where neighbouring rows of one genome end up in one CTA - and asking for the next row at the start
+    // of a pass - 7-10 % slower.)
     for (;;) {
         int r0 = 0;
         if (lane == 0) r0 = (int)atomicAdd(&a.st->row_counter, (unsigned)RPW);
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
         if (lane == 0 && total > 0) base = (long long)atomicAdd(&a.st->cursor, (unsigned long long)total);
 
         const int maxcnt = __reduce_max_sync(kFull, cnt);
-        double s1 = 0.0;
+        Sq128 pos = {0ull, 0ull}, neg = {0ull, 0ull};
         int nz = 0;
         for (int b = 0; b < maxcnt; b += G) {
             const int i = b + sub;
@@ -324,20 +328,19 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
                 v = mul_rn(a.scale, tval[slot]);
                 if (slot == dslot) v = add_rn(v, a.restart);
                 tval[slot] = v;
-                s1 += (double)v * (double)v;
+                sq_add(pos, (double)v * (double)v);
                 one = v != (T)0;
             }
             nz += __popc(__ballot_sync(kFull, one) & gmask);
             if (a.hist) hist_values<T>(a.hist, win, one, v, pred_valid, pred0);
         }
         if (diag_new) {
-            if (sub == 0) s1 += (double)a.restart * (double)a.restart;
+            if (sub == 0) sq_add(pos, (double)a.restart * (double)a.restart);
             if (a.restart != (T)0) nz += 1;
         }
         if (a.hist && __any_sync(kFull, diag_new))
             hist_values<T>(a.hist, win, diag_new && sub == 0 && a.restart != (T)0, a.restart, pred_valid, pred0);
         __syncwarp();
-        double s2 = 0.0;
         for (int b = 0; b < maxnk; b += G) {
             const int idx = b + sub;
             if (idx < nk_live) {
@@ -349,25 +352,15 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
                 if (found) newv = tval[slot];
                 else if (j == dcol) newv = a.restart;
                 const T d = sub_rn(oldv, newv);
-                s2 += (double)d * (double)d - (double)newv * (double)newv;
+                sq_add(pos, (double)d * (double)d);
+                sq_add(neg, (double)newv * (double)newv);
             }
         }
-        double rowsq = s1 + s2;
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) rowsq += __shfl_xor_sync(kFull, rowsq, o);
+        const Sq128 rowsq = sq_diff(sq_group_sum(pos, G), sq_group_sum(neg, G));
         if (live && sub == 0) {
-            // same fixed-point limbs as totals_add_rowsq
-            double x = rowsq;
-            if (x > 0.0) {
-                if (x >= 4294967296.0) x = 4294967295.0;
-                const double hi = floor(x);
-                const double f1 = (x - hi) * 4294967296.0;
-                const double m1 = floor(f1);
-                const double m0 = floor((f1 - m1) * 4294967296.0);
-                t_sq2 += (unsigned long long)hi;
-                t_sq1 += (unsigned long long)m1;
-                t_sq0 += (unsigned long long)m0;
-            }
+            t_sq2 += rowsq.hi;
+            t_sq1 += rowsq.lo >> 32;
+            t_sq0 += rowsq.lo & 0xffffffffull;
             t_kept += (unsigned long long)nk;
             t_nnz += (unsigned long long)nz;
             t_max_len = max(t_max_len, nz);
@@ -410,6 +403,7 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
         for (int i = sub; i < cnt; i += G) tkey[ord[i]] = -1;
         __syncwarp();
     }
+    pdl_launch_dependents();        // this warp is out of rows: the next kernel's CTAs may take the SM as it empties
 
     // ---- publish the warp's totals
 #pragma unroll
@@ -422,17 +416,32 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
     }
     t_max_kept = __reduce_max_sync(kFull, t_max_kept);
     t_max_len = __reduce_max_sync(kFull, t_max_len);
+    // one set of global atomics per CTA: the warps meet in shared memory first
+    __shared__ unsigned long long s_tot[5];
+    __shared__ int s_max[2];
+    if (threadIdx.x < 5) s_tot[threadIdx.x] = 0ull;
+    if (threadIdx.x < 2) s_max[threadIdx.x] = 0;
+    __syncthreads();
     if (lane == 0) {
-        WalkState* st = a.st;
-        if (t_sq0) atomicAdd(&st->sq_limb[0], t_sq0);
-        if (t_sq1) atomicAdd(&st->sq_limb[1], t_sq1);
-        if (t_sq2) atomicAdd(&st->sq_limb[2], t_sq2);
-        if (t_nnz) atomicAdd(&st->nnz_exact, t_nnz);
-        if (t_kept) atomicAdd(&st->nnz_in, t_kept);
-        if (t_max_kept) atomicMax(&st->max_kept, t_max_kept);
-        if (t_max_len) atomicMax(&st->max_row_len, t_max_len);
+        if (t_sq0) atomicAdd(&s_tot[0], t_sq0);
+        if (t_sq1) atomicAdd(&s_tot[1], t_sq1);
+        if (t_sq2) atomicAdd(&s_tot[2], t_sq2);
+        if (t_nnz) atomicAdd(&s_tot[3], t_nnz);
+        if (t_kept) atomicAdd(&s_tot[4], t_kept);
+        if (t_max_kept) atomicMax(&s_max[0], t_max_kept);
+        if (t_max_len) atomicMax(&s_max[1], t_max_len);
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        WalkState* st = a.st;
+        if (s_tot[0]) atomicAdd(&st->sq_limb[0], s_tot[0]);
+        if (s_tot[1]) atomicAdd(&st->sq_limb[1], s_tot[1]);
+        if (s_tot[2]) atomicAdd(&st->sq_limb[2], s_tot[2]);
+        if (s_tot[3]) atomicAdd(&st->nnz_exact, s_tot[3]);
+        if (s_tot[4]) atomicAdd(&st->nnz_in, s_tot[4]);
+        if (s_max[0]) atomicMax(&st->max_kept, s_max[0]);
+        if (s_max[1]) atomicMax(&st->max_row_len, s_max[1]);
+    }
     if (a.hist) hist_window_flush<T>(a.hist, win);
 }
 

@@ -532,6 +532,8 @@ template <typename T>
 __global__ void __launch_bounds__(512) select_hist_kernel(const T* vals, WalkState* st, unsigned long long* __restrict__ hist,
                                                           int level, int fused_tail) {
     __shared__ unsigned int sh[kSelectBins];
+    pdl_wait();
+    pdl_launch_dependents();
     if (st->done) return;
     if (level == 1 && st->hist1_ready) return;      // the propagate epilogue already filled this level and it was scanned
     // lumped-window miss (unsharded walk): the percentile's level-0 bin is unknown - this pass counts level 0 in full and
@@ -592,6 +594,8 @@ template <typename T>
 __global__ void __launch_bounds__(512) select_gather_kernel(const T* vals, WalkState* st, unsigned long long* __restrict__ block,
                                                             unsigned long long cand_cap, int fused, FinishArgs fin) {
     __shared__ __align__(16) unsigned char scratch[kFinishScratchBytes];
+    pdl_wait();
+    pdl_launch_dependents();
     if (st->done) return;
     gather_pass<T>(vals, (long long)st->cursor, (typename KeyOf<T>::type)st->prefix, block, cand_cap, st->prefix_bits);
     if (fused && last_block(&st->tick_gather)) finish_step_body<T>(fin, scratch);
@@ -600,6 +604,8 @@ __global__ void __launch_bounds__(512) select_gather_kernel(const T* vals, WalkS
 template <typename T>
 __global__ void __launch_bounds__(1024) finish_step_kernel(FinishArgs a) {
     __shared__ __align__(16) unsigned char scratch[kFinishScratchBytes];
+    pdl_wait();
+    pdl_launch_dependents();
     if (a.st->done) return;
     finish_step_body<T>(a, scratch);
 }
