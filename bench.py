@@ -341,7 +341,7 @@ def main():
         dom_us = 1e3 * kern_ms / max(kern_launches, 1)
         achieved = total_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     else:
-        dom_name, dom_bytes, dom_us, achieved = "propagate_kernel", prop_bytes_launch, 1e3 * prop_ms_per_launch, prop_achieved
+        dom_name, dom_bytes, dom_us, achieved = "propagate_group_kernel (walk steps >= 1; step 0 runs propagate_kernel)", prop_bytes_launch, 1e3 * prop_ms_per_launch, prop_achieved
     h2d = M.indptr.size * 8 + M.indices.size * 4 + M.data.size * 8 + n * 4
     traffic, traffic_src = measured_traffic(args.workload, args.dtype) if world == 1 else (None, None)
 

@@ -74,11 +74,13 @@ def markers_first_order(n_contigs: int, marker_idx_sorted) -> np.ndarray:
     same order from a boolean mask.
     """
     marker_idx_sorted = np.asarray(marker_idx_sorted, dtype=np.int64)
+    m = marker_idx_sorted.size
     rest = np.ones(n_contigs, dtype=bool)
     rest[marker_idx_sorted] = False
-    perm = np.concatenate([marker_idx_sorted, np.nonzero(rest)[0]])
-    new_of_old = np.empty(n_contigs, dtype=np.int32)
-    new_of_old[perm] = np.arange(n_contigs, dtype=np.int32)
+    # non-markers keep their order behind the m markers: position = m + (number of non-markers before i)
+    new_of_old = np.cumsum(rest, dtype=np.int32)
+    new_of_old += np.int32(m - 1)
+    new_of_old[marker_idx_sorted] = np.arange(m, dtype=np.int32)
     return new_of_old
 
 
@@ -420,6 +422,34 @@ class Walker:
         return sp.csr_matrix((dt.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()), shape=(self.rows, self.n))
 
 
+_PINNED = {}
+
+
+def _pinned(dtype, n: int):
+    """A pinned host staging buffer of at least n elements (cached per dtype: cudaHostAlloc is slow)."""
+    torch = _torch()
+    buf = _PINNED.get(dtype)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(int(n * 1.5), 1 << 16), dtype=dtype).pin_memory()
+        _PINNED[dtype] = buf
+    return buf
+
+
+def download_csr(indptr, indices, data, shape) -> sp.csr_matrix:
+    """Device CSR triplets -> scipy CSR with ONE stream synchronisation (three staged asynchronous copies)."""
+    torch = _torch()
+    if indptr.dtype == data.dtype or indices.dtype == data.dtype or not data.is_cuda:
+        return sp.csr_matrix((data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()), shape=shape)
+    views = []
+    for t in (indptr, indices, data):
+        host = _pinned(t.dtype, t.numel())[:t.numel()]
+        host.copy_(t, non_blocking=True)
+        views.append(host)
+    torch.cuda.current_stream(data.device).synchronize()
+    ip, ix, dt = (v.numpy().copy() for v in views)          # the staging buffers are reused by the next call
+    return sp.csr_matrix((dt, ix, ip), shape=shape)
+
+
 def symmetrise_device(indptr, indices, data, m: int):
     """imputation.py:122-127 on device tensors of an m x m CSR matrix with sorted rows."""
     torch = _torch()
@@ -446,7 +476,7 @@ def symmetrise_device(indptr, indices, data, m: int):
                                              C.c_void_p(dt.data_ptr()), nnz, C.c_void_p(scratch.data_ptr()), nbytes,
                                              C.c_void_p(e_ip.data_ptr()), C.c_void_p(e_ix.data_ptr()),
                                              C.c_void_p(e_dt.data_ptr()), stream))
-        torch.cuda.current_stream(device).synchronize()
+        # stream-ordered: scratch and inputs are returned to torch's allocator, which reuses them on this stream only
     return e_ip, e_ix[:n], e_dt[:n]
 
 
@@ -461,7 +491,8 @@ def symmetrise_normalise(Q, device=None) -> sp.csr_matrix:
     ix = torch.from_numpy(Q.indices.astype(np.int32)).to(device)
     dt = torch.from_numpy(np.ascontiguousarray(Q.data)).to(device)
     e_ip, e_ix, e_dt = symmetrise_device(ip, ix, dt, m)
-    return sp.csr_matrix((e_dt.cpu().numpy(), e_ix.cpu().numpy(), e_ip.cpu().numpy()), shape=(m, m))
+    with torch.cuda.device(device):
+        return download_csr(e_ip, e_ix, e_dt, (m, m))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -515,14 +546,22 @@ def crwr_impute(normcc, marker_idx_sorted, rp, perc, tol: float = DEFAULT_TOL, m
         M.sum_duplicates()
     idx = np.asarray(marker_idx_sorted, dtype=np.int64)
     n, m = M.shape[0], idx.size
-    new_of_old = markers_first_order(n, idx)
     w = Walker(n, m, dtype=dtype, device=device, transition_nnz_cap=int(M.nnz) + n)
     try:
-        nnz_p = w.build_transition(M.indptr, M.indices, M.data, new_of_old)
-        st = w.walk(rp, perc, tol, max_steps)
-        ip, ix, dt = w.result_device()
-        e_ip, e_ix, e_dt = symmetrise_device(ip, ix, dt, m)
-        E = sp.csr_matrix((e_dt.cpu().numpy(), e_ix.cpu().numpy(), e_ip.cpu().numpy()), shape=(m, m))
+        torch = _torch()
+        with torch.cuda.device(w.device):
+            # the matrix goes up first (asynchronous from pinned memory); the markers-first order is computed on the
+            # host while the copies run
+            d_ip = w._to_device(M.indptr, torch.int64)
+            d_ix = w._to_device(M.indices, torch.int32)
+            d_dt = w._to_device(M.data, torch.float64)
+            new_of_old = markers_first_order(n, idx)
+            nnz_p = w.build_transition(d_ip, d_ix, d_dt, new_of_old)
+            del d_ip, d_ix, d_dt
+            st = w.walk(rp, perc, tol, max_steps)
+            ip, ix, dt = w.result_device()
+            e_ip, e_ix, e_dt = symmetrise_device(ip, ix, dt, m)
+            E = download_csr(e_ip, e_ix, e_dt, (m, m))
         info = WalkInfo(int(st.steps_done), _lib.STOP_NAMES.get(int(st.stop_reason), "?"), w.trace() if return_info else [],
                         nnz_p, w.regrows)
     finally:

@@ -47,6 +47,7 @@ static long long g_launches = 0;
 namespace {
 
 constexpr int kDenseWarpsPerCta = 4;
+constexpr int kOrderStep = 4;       // first walk step that hands rows out longest first (row lengths have settled by then)
 
 // Launch with programmatic stream serialization (see pdl_wait in common.cuh) when `pdl`, else the ordinary way.
 template <typename... KArgs, typename... Args>
@@ -67,7 +68,7 @@ cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, 
 struct Layout {
     size_t state, trace, p_indptr, p_cols, p_vals;
     size_t it_cols[2], it_vals[2], it_ptr[2], it_len[2];
-    size_t fb_rows, xbuf, cand, merged, gathered, counts, counts_scan, total;
+    size_t fb_rows, row_order, xbuf, cand, merged, gathered, counts, counts_scan, total;
     size_t d_acc, d_oldv, d_ord, d_tbits, d_kbits;
     size_t k1_row_cnt, k1_col_cnt, k1_col_ptr, k1_col_fill, k1_csc_row, k1_csc_val, k1_scale, k1_iso, k1_row_val;
     size_t k1_bad;
@@ -104,6 +105,7 @@ bool make_layout(const crwr_config& c, Layout& L) {
         L.it_len[b] = bump(off, 4 * (size_t)rows);
     }
     L.fb_rows = bump(off, 4 * (size_t)rows);
+    L.row_order = bump(off, 4 * (size_t)rows);
     // exchange buffer: [extras (kXExtras) | level-0 histogram | level-1 histogram], all uint64
     L.xbuf = bump(off, 8 * (size_t)(kXExtras + kSelectLevels * kSelectBins));
     // candidate block [count, successor, keys...]; sharded walks use a small fixed block (all-gathered)
@@ -159,6 +161,8 @@ struct crwr_handle_s {
     GroupShape gshape;              // run-time sizing of the row-group propagate kernel (default)
     int ggrid = 0;                  // its persistent grid size
     int prop_kind = 1;              // 1: row-group kernel (default), 0: warp-per-row kernel (CRWR_PROP=warp)
+    bool order_valid = false;       // row_order holds the longest-first order of this walk (built before step kOrderStep)
+    bool use_order = true;          // CRWR_ROW_ORDER=0: rows in index order
     int pdl_forced = -1;            // CRWR_PDL=0/1: programmatic dependent launch forced off/on (-1: by row length, use_pdl)
     // 0 (default): one launch per phase.  1: one cooperative kernel per chunk of steps - measured equal for
     // float32 small-row workloads and 10-15 % slower for float64 (small CTAs make CTA 0's serial scan/finish
@@ -392,6 +396,7 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     a.fused_select = fused ? 1 : 0;
     a.prefill_l1 = fused ? 1 : 0;
     a.part = nullptr;                           // lumped level-0 window: not enabled
+    a.row_order = h->order_valid ? h->at<int32_t>(L.row_order) : nullptr;
     // a warp reserves output space for a few rows at a time (zero-padded leftovers are skipped by the select)
     {
         long long ch = 3 * (long long)h->hint_len_eff;
@@ -421,6 +426,13 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, cudaStream_t st) 
     if (h->profile) {
         if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
         cudaEventRecord(e0, st);
+    }
+    if (h->prop_kind == 1 && h->use_order && !h->order_valid && h->steps_enqueued >= kOrderStep && rows >= 64) {
+        // the walk has settled (the host sized the kernels from the third poll): rows by length, once
+        row_order_kernel<<<1, 1024, 0, st>>>(h->at<int32_t>(h->L.it_len[parity]), rows, h->at<int32_t>(h->L.row_order));
+        ++g_launches;
+        h->order_valid = true;
+        a.row_order = h->at<int32_t>(h->L.row_order);
     }
     if (h->prop_kind == 1 && h->steps_enqueued >= 1) {      // step 0 keeps scipy's storage order (warp-per-row kernel)
         const GroupShape& sh = h->gshape;
@@ -743,6 +755,7 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     }
     if (const char* k = getenv("CRWR_PROP")) h->prop_kind = strcmp(k, "warp") == 0 ? 0 : 1;
     if (const char* k = getenv("CRWR_PDL")) h->pdl_forced = atoi(k) != 0 ? 1 : 0;
+    if (const char* k = getenv("CRWR_ROW_ORDER")) h->use_order = atoi(k) != 0;
     *out = h;
     return CRWR_OK;
 }
@@ -871,6 +884,7 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     h->rp = rp;
     h->perc = perc;
     h->steps_enqueued = 0;
+    h->order_valid = false;
     h->walking = true;
     h->mode = h->mode_next;
     return CRWR_OK;

@@ -40,6 +40,7 @@ struct PropArgs {
     int32_t chunk;              // entries a warp reserves from the product buffer at a time
     int32_t row_chunk;          // rows a warp takes from the row counter at a time
     int32_t prefill_l1;         // 1: also count level 1 for the level-0 bin predicted from the previous cut
+    const int32_t* row_order;   // row-group kernel: rows in the order they are handed out (longest first), or null
     StepPartial* part;          // unsharded row-group steps: level 0 goes to the lumped window of these kRep replicas
                                 // (with the step totals) instead of `hist`; null otherwise
 };

@@ -78,6 +78,56 @@ __device__ __forceinline__ void group_sort_pairs(int32_t* key, T* val, int n, in
     }
 }
 
+// Longest rows first: a one-off counting sort of the rows by the length of their current iterate row, run once the
+// walk has settled (the lengths barely move afterwards).  The row counter then hands out the heavy rows first and the
+// lightest last, so the kernel does not end on a long row that started late, and the rows sharing a warp are of
+// similar weight.  Order inside a length bucket is arbitrary: the order of processing never affects a value.
+__global__ void __launch_bounds__(1024) row_order_kernel(const int32_t* __restrict__ row_len, int n_rows, int32_t* __restrict__ order) {
+    constexpr int NB = 2048;
+    __shared__ int cnt[NB];
+    __shared__ int warp_tot[32];
+    const int t = threadIdx.x;
+    for (int i = t; i < NB; i += 1024) cnt[i] = 0;
+    __syncthreads();
+    // bucket 0 = longest
+    for (int r = t; r < n_rows; r += 1024) {
+        int len = row_len[r];
+        len = len < 0 ? 0 : (len > NB - 1 ? NB - 1 : len);
+        atomicAdd(&cnt[NB - 1 - len], 1);
+    }
+    __syncthreads();
+    // exclusive scan of the 2048 counts: 2 per thread
+    const int a0 = cnt[2 * t], a1 = cnt[2 * t + 1];
+    int incl = a0 + a1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, o);
+        if ((t & 31) >= o) incl += v;
+    }
+    if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        const int w = warp_tot[t];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, wi, o);
+            if (t >= o) wi += v;
+        }
+        warp_tot[t] = wi - w;
+    }
+    __syncthreads();
+    const int excl = warp_tot[t >> 5] + incl - (a0 + a1);
+    cnt[2 * t] = excl;
+    cnt[2 * t + 1] = excl + a0;
+    __syncthreads();
+    for (int r = t; r < n_rows; r += 1024) {
+        int len = row_len[r];
+        len = len < 0 ? 0 : (len > NB - 1 ? NB - 1 : len);
+        order[atomicAdd(&cnt[NB - 1 - len], 1)] = r;
+    }
+}
+
 template <typename T, int G>
 __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, GroupShape sh) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -147,8 +197,8 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
         if (lane == 0) r0 = (int)atomicAdd(&a.st->row_counter, (unsigned)RPW);
         r0 = __shfl_sync(kFull, r0, 0);
         if (r0 >= a.n_rows) break;
-        const int row = r0 + grp;
-        const bool has_row = row < a.n_rows;
+        const bool has_row = r0 + grp < a.n_rows;
+        const int row = (has_row && a.row_order) ? __ldg(a.row_order + r0 + grp) : r0 + grp;
 
         // ---- read the row, dropping entries at or below the previous cut (strict >, utility.py:290).
         // With a cut the kept entries must be consumed in column order (`Q > cut` sorts the operand,
