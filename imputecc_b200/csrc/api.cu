@@ -68,7 +68,7 @@ cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, 
 struct Layout {
     size_t state, trace, p_indptr, p_cols, p_vals;
     size_t it_cols[2], it_vals[2], it_ptr[2], it_len[2];
-    size_t fb_rows, row_order, xbuf, cand, merged, gathered, counts, counts_scan, total;
+    size_t fb_rows, row_order, scan_tmp, xbuf, cand, merged, gathered, counts, counts_scan, total;
     size_t d_acc, d_oldv, d_ord, d_tbits, d_kbits;
     size_t k1_row_cnt, k1_col_cnt, k1_col_ptr, k1_col_fill, k1_csc_row, k1_csc_val, k1_scale, k1_iso, k1_row_val;
     size_t k1_bad;
@@ -106,6 +106,7 @@ bool make_layout(const crwr_config& c, Layout& L) {
     }
     L.fb_rows = bump(off, 4 * (size_t)rows);
     L.row_order = bump(off, 4 * (size_t)rows);
+    L.scan_tmp = bump(off, 8 * (size_t)kScanMaxTiles);
     // exchange buffer: [extras (kXExtras) | level-0 histogram | level-1 histogram], all uint64
     L.xbuf = bump(off, 8 * (size_t)(kXExtras + kSelectLevels * kSelectBins));
     // candidate block [count, successor, keys...]; sharded walks use a small fixed block (all-gathered)
@@ -362,6 +363,20 @@ int configure_group_shape(crwr_handle_s* h, long long max_row_len, long long max
 }
 
 unsigned long long* hist_ptr(crwr_handle_s* h);
+
+// Exclusive scan of n int32 counts into n+1 int32 offsets: many CTAs when the input is long.
+void launch_scan_i32(crwr_handle_s* h, const int32_t* cnt, int32_t* out, long long n, long long* total_out, cudaStream_t st) {
+    const long long tiles = (n + kScanTile - 1) / kScanTile;
+    if (tiles >= 2 && tiles <= kScanMaxTiles) {
+        long long* tmp = h->at<long long>(h->L.scan_tmp);
+        scan_tile_sums_kernel<<<(int)tiles, 1024, 0, st>>>(cnt, n, tmp);
+        scan_tiles_kernel<int32_t><<<(int)tiles, 1024, 0, st>>>(cnt, out, n, tmp, total_out);
+        g_launches += 2;
+    } else {
+        exclusive_scan_kernel<int32_t><<<1, 1024, 0, st>>>(cnt, out, n, total_out);
+        ++g_launches;
+    }
+}
 
 // Programmatic dependent launch of the step kernels (common.cuh, pdl_wait): hides the launch gaps between the four
 // dependent kernels of a step.  Measured on B200: -9 % per step at ~100-entry rows (90 -> 81 us), +4 % at ~650-entry
@@ -799,14 +814,12 @@ int32_t crwr_build_transition(crwr_handle h, const int64_t* d_indptr, const int3
     const int warp_grid = (int)((n * 32 + tb - 1) / tb);
     transition_count_kernel<<<rows_grid, tb, 0, st>>>(d_indptr, d_indices, d_data, d_new_of_old, n, sc);
     LAUNCH_CHECK();
-    exclusive_scan_kernel<int32_t><<<1, 1024, 0, st>>>(sc.col_cnt, sc.col_ptr, n, nullptr);
-    LAUNCH_CHECK();
+    launch_scan_i32(h, sc.col_cnt, sc.col_ptr, n, nullptr, st);
     transition_scatter_kernel<<<rows_grid, tb, 0, st>>>(d_indptr, d_indices, d_data, d_new_of_old, n, sc);
     LAUNCH_CHECK();
     transition_colsum_kernel<<<warp_grid, tb, 0, st>>>(n, sc);
     LAUNCH_CHECK();
-    exclusive_scan_kernel<int32_t><<<1, 1024, 0, st>>>(sc.row_cnt, h->at<int32_t>(L.p_indptr), n, sc.total);
-    LAUNCH_CHECK();
+    launch_scan_i32(h, sc.row_cnt, h->at<int32_t>(L.p_indptr), n, sc.total, st);
     if (h->cfg.dtype == CRWR_F64)
         transition_fill_kernel<double><<<warp_grid, tb, 0, st>>>(d_indptr, d_indices, d_data, d_new_of_old, n, sc,
                                                                  h->at<int32_t>(L.p_indptr), h->at<int32_t>(L.p_cols),

@@ -70,6 +70,93 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
     }
 }
 
+// The same scan over many CTAs for long inputs (the single-CTA form takes ~40 us at 50,000 counts): pass 1 sums
+// tiles of 8192 counts, pass 2 gives every tile the sum of the tiles before it and scans the tile.
+constexpr int kScanTile = 8192;
+constexpr int kScanMaxTiles = 4096;
+
+__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const int32_t* __restrict__ cnt, long long n,
+                                                               long long* __restrict__ tile_sum) {
+    __shared__ long long warp_tot[32];
+    const int t = threadIdx.x;
+    const long long i0 = (long long)blockIdx.x * kScanTile + (long long)t * 8;
+    long long mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mine += (i0 + k < n) ? (long long)cnt[i0 + k] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFull, mine, o);
+    if ((t & 31) == 0) warp_tot[t >> 5] = mine;
+    __syncthreads();
+    if (t < 32) {
+        long long w = warp_tot[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(kFull, w, o);
+        if (t == 0) tile_sum[blockIdx.x] = w;
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(const int32_t* __restrict__ cnt, OutT* __restrict__ out, long long n,
+                                                          const long long* __restrict__ tile_sum, long long* total_out) {
+    constexpr int ITEMS = 8;
+    __shared__ long long warp_tot[32];
+    __shared__ long long carry_s;
+    const int t = threadIdx.x;
+    // sum of the tiles before this one
+    long long before = 0;
+    for (int i = t; i < (int)blockIdx.x; i += 1024) before += tile_sum[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(kFull, before, o);
+    if ((t & 31) == 0) warp_tot[t >> 5] = before;
+    __syncthreads();
+    if (t < 32) {
+        long long w = warp_tot[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(kFull, w, o);
+        if (t == 0) carry_s = w;
+    }
+    __syncthreads();
+    const long long carry = carry_s;
+    __syncthreads();
+    const long long i0 = (long long)blockIdx.x * kScanTile + (long long)t * ITEMS;
+    long long v[ITEMS];
+    long long mine = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        v[k] = (i0 + k < n) ? (long long)cnt[i0 + k] : 0;
+        mine += v[k];
+    }
+    long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long w = __shfl_up_sync(kFull, incl, o);
+        if ((t & 31) >= o) incl += w;
+    }
+    if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        long long w = warp_tot[t];
+        long long wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long x = __shfl_up_sync(kFull, wi, o);
+            if (t >= o) wi += x;
+        }
+        warp_tot[t] = wi - w;
+    }
+    __syncthreads();
+    long long run = carry + warp_tot[t >> 5] + incl - mine;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (i0 + k < n) out[i0 + k] = (OutT)run;
+        run += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && t == 1023) {       // the last thread of the last tile holds the grand total
+        out[n] = (OutT)run;
+        if (total_out) *total_out = run;
+    }
+}
+
 struct TransitionScratch {
     int32_t* row_cnt;     // [N+1] entries of B per new row
     int32_t* col_cnt;     // [N+1] entries of A per new column

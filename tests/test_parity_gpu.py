@@ -68,6 +68,21 @@ def test_transition_matrix(cuda_device, name, dtype):
         assert _bit_equal(P, load_csr(rec, "P32"))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_transition_matrix_many_tiles(cuda_device, dtype):
+    """N large enough for the multi-CTA offset scans of the build (tiles of 8192 contigs)."""
+    M, idx = synth.make_workload(synth.Workload("t20k", 20000, 3200, 100, 16))
+    w = pkg.Walker(M.shape[0], len(idx), dtype=dtype, device=cuda_device, transition_nnz_cap=M.nnz + M.shape[0])
+    try:
+        w.build_transition(M.indptr, M.indices, M.data, pkg.markers_first_order(M.shape[0], idx))
+        P = w.transition()
+    finally:
+        w.close()
+    want = oracle.transition_matrix(M, oracle.marker_permutation(M.shape[0], idx), dtype)
+    assert P.dtype == dtype and P.has_sorted_indices
+    assert _bit_equal(P, want)
+
+
 # ---------------------------------------------------------------------------------------------
 # B-inner: random_walk_b200 == random_walk_cpu
 # ---------------------------------------------------------------------------------------------
