@@ -192,6 +192,35 @@ def test_c2_sized_walk_against_live_oracle(cuda_device, dtype):
     assert (Es != Es.T).nnz == 0 or asym.max() <= 4 * np.finfo(dtype).eps * Es.max()
 
 
+@pytest.mark.parametrize("perc", [50, 80, 95])
+@pytest.mark.parametrize("rp", [0.3, 0.5, 0.7])
+def test_parameter_sweep_against_live_oracle(cuda_device, rp, perc):
+    """BASELINE config 5 (rwr-rp x rwr-thres sweep) at a size the oracle walks in a fraction of a second: the imputed
+    matrix is bit-identical in float32, so anything computed from it downstream (preliminary bins) is identical too."""
+    M, idx = synth.make_workload(synth.Workload("sweep", 4000, 640, 100, 16))
+    E, info = pkg.crwr_impute(M, idx, rp, perc, dtype=np.float32, device=cuda_device, return_info=True)
+    tr = oracle.WalkTrace()
+    want = oracle.crwr_impute(M, idx, rp, perc, dtype=np.float32, trace=tr)
+    assert info.steps == len(tr.steps) and info.stop_reason == tr.stop_reason
+    assert [(t["nnz_in"], t["nnz_new"]) for t in info.trace] == [(t.nnz_in, t.nnz_new) for t in tr.steps]
+    assert _bit_equal(sp.csr_matrix(E), sp.csr_matrix(want))
+
+
+@pytest.mark.parametrize("name", ["c2_sparse", "c3_sparse", "c3_dense"])
+def test_baseline_sized_workloads_bit_identical_to_live_oracle(cuda_device, name):
+    """The bench workloads themselves (BASELINE configs 2 and 3, SURVEY.md 8d generator), float32 as the reference
+    computes: every kernel shape the bench runs (row-group kernel at 2 and 1 rows per warp, longest-first order,
+    multi-CTA scans) against the scipy walk on the same matrix.  The oracle takes ~0.5 / 2 / 11 s."""
+    M, idx = synth.make_workload(synth.WORKLOADS[name])
+    E, info = pkg.crwr_impute(M, idx, 0.5, 80, dtype=np.float32, device=cuda_device, return_info=True)
+    tr = oracle.WalkTrace()
+    want = oracle.crwr_impute(M, idx, 0.5, 80, dtype=np.float32, trace=tr)
+    assert info.steps == len(tr.steps) and info.stop_reason == tr.stop_reason
+    assert [(t["nnz_in"], t["nnz_new"]) for t in info.trace] == [(t.nnz_in, t.nnz_new) for t in tr.steps]
+    assert all(t["fallback_rows"] == 0 for t in info.trace[4:])      # the sizing hints keep the settled walk off the slow path
+    assert _bit_equal(sp.csr_matrix(E), sp.csr_matrix(want))
+
+
 def test_result_is_independent_of_kernel_sizing_and_large_row_path(cuda_device):
     """Any accumulator sizing - including one so small that most rows take the dense large-row
     kernel - must give the same bits."""
