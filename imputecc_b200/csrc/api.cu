@@ -423,7 +423,6 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     a.hist = fused ? hist_ptr(h) : nullptr;
     a.fused_select = fused ? 1 : 0;
     a.prefill_l1 = fused ? 1 : 0;
-    a.part = nullptr;                           // lumped level-0 window: not enabled
     a.row_order = h->order_valid ? h->at<int32_t>(L.row_order) : nullptr;
     // a warp reserves output space for a few rows at a time (zero-padded leftovers are skipped by the select)
     {
@@ -545,7 +544,6 @@ FinishArgs finish_args(crwr_handle_s* h, int do_select, const void* gathered) {
     a.cand_cap = (unsigned long long)L.cand_cap;
     a.trace = h->at<crwr_step_record>(L.trace);
     a.do_select = do_select;
-    a.part = nullptr;
     return a;
 }
 

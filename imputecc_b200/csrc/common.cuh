@@ -14,8 +14,6 @@ constexpr int kCandSmem = 4096;                 // candidates ranked inside shar
 constexpr int kMaxTrace = 4096;                 // per-step records kept on the device
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kHistWin = 512;                   // level-0 bins kept in a per-CTA shared-memory window
-constexpr int kLWin = 64;                       // lumped window (unsharded walk): level-0 bins counted around the previous cut
-constexpr int kRep = 32;                        // replicas of the per-step partial sums (CTAs spread their atomics over them)
 
 // ---------------------------------------------------------------------------------------------
 // Exact (non-contracted) arithmetic.  scipy's csr_matmat does `sums[j] += v * B[k,j]` as a
@@ -120,24 +118,7 @@ struct WalkState {
     unsigned long long phase_ns[8];    // persistent kernel: summed nanoseconds per phase (CTA 0's view), diagnostics
     int32_t scan_done;                 // the level scans of this step already ran (in the propagate kernel's last CTA)
     int32_t unordered_rows;            // the row-group kernel wrote this step's rows in slot-claim order (valid only behind a cut)
-    // lumped level-0 window of the unsharded walk (StepPartial): only the kLWin bins [win_lo, win_lo + kLWin) around the
-    // previous cut are counted one by one, everything below / above is lumped into two counters
-    int32_t win_lo;                    // first level-0 bin of the window
-    int32_t win_valid;                 // a previous cut exists: the window is meaningful
-    int32_t hist_miss;                 // this step's percentile fell outside the window: redo level 0 with a full pass
-    int32_t prefix_bits;               // key bits fixed by the scans when the gather runs (24, or 12 after a miss)
 };
-
-// Per-step partial sums of the unsharded walk, kRep replicas: a CTA adds to replica blockIdx % kRep so that
-// thousands of CTAs do not serialise on one L2 line; the scan after the propagate kernel folds them.
-struct StepPartial {
-    unsigned int win[kLWin];           // level-0 counts of the window bins
-    unsigned int below, above;         // values under the window / at or above its end
-    int32_t max_kept, max_len;
-    unsigned long long sq[3], nnz, kept;
-    unsigned long long pad[9];         // 384 bytes: replicas start on their own 128-byte lines
-};
-static_assert(sizeof(StepPartial) == 384, "StepPartial layout");
 
 // Exchange block 0 of a sharded walk: level-0 histogram followed by these extras (all uint64, SUM).
 constexpr int kXSq0 = 0, kXSq1 = 1, kXSq2 = 2, kXNnzIn = 3, kXNnzNew = 4, kXCapOvf = 5, kXSelOvf = 6, kXFallback = 7;

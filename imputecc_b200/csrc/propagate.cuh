@@ -41,8 +41,6 @@ struct PropArgs {
     int32_t row_chunk;          // rows a warp takes from the row counter at a time
     int32_t prefill_l1;         // 1: also count level 1 for the level-0 bin predicted from the previous cut
     const int32_t* row_order;   // row-group kernel: rows in the order they are handed out (longest first), or null
-    StepPartial* part;          // unsharded row-group steps: level 0 goes to the lumped window of these kRep replicas
-                                // (with the step totals) instead of `hist`; null otherwise
 };
 
 // Fused select, unsharded walk: once every value of the step is in the level-0 histogram, one CTA locates
@@ -208,25 +206,6 @@ __device__ __forceinline__ void hist_window_flush(unsigned long long* hist, cons
         const unsigned c = win[i];
         if (c) atomicAdd(&hist[HistWindow<T>::base + i], (unsigned long long)c);
     }
-}
-
-// Lumped-window form of the level-0 count (unsharded walk, see StepPartial), straight to global memory: used by
-// the large-row kernel, whose rows are few.  Level 1 is pre-filled for the predicted bin as in hist_values.
-template <typename T>
-__device__ __forceinline__ void hist_lumped_global(StepPartial* rep, unsigned long long* hist, int win_lo, bool win_valid,
-                                                   bool valid, T v, bool pred_valid, typename KeyOf<T>::type pred0) {
-    typedef KeyOf<T> KO;
-    if (!valid) return;
-    const typename KO::type key = KO::enc(v);
-    const typename KO::type bin0 = key >> (KO::bits - kSelectBits);
-    if (win_valid) {
-        const int d = (int)bin0 - win_lo;
-        if (d < 0) atomicAdd(&rep->below, 1u);
-        else if (d >= kLWin) atomicAdd(&rep->above, 1u);
-        else atomicAdd(&rep->win[d], 1u);
-    }
-    if (pred_valid && bin0 == pred0)
-        atomicAdd(&hist[kSelectBins + ((unsigned)(key >> (KO::bits - 2 * kSelectBits)) & (kSelectBins - 1))], 1ull);
 }
 
 __device__ __forceinline__ uint32_t hash_col(int32_t j, int log_h) {
@@ -711,9 +690,6 @@ __device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScra
     const T cut = (T)__ldcg(&a.st->cut);
     const bool pred_valid = a.prefill_l1 && __ldcg(&a.st->pred_valid) != 0;
     const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)__ldcg(&a.st->pred_prefix0);
-    const int win_lo = __ldcg(&a.st->win_lo);
-    const bool win_valid = __ldcg(&a.st->win_valid) != 0;
-    StepPartial* rep = a.part ? a.part + (blockIdx.x % kRep) : nullptr;
     WarpTotals wt;
     totals_init(wt);
 
@@ -792,14 +768,12 @@ __device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScra
                 one = v != (T)0;
             }
             nz += __popc(__ballot_sync(kFull, one));
-            if (rep) hist_lumped_global<T>(rep, a.hist, win_lo, win_valid, one, v, pred_valid, pred0);
-            else if (a.hist) hist_values<T>(a.hist, win, one, v, pred_valid, pred0);
+            if (a.hist) hist_values<T>(a.hist, win, one, v, pred_valid, pred0);
         }
         if (diag_new) {
             if (lane == 0) sq_add(pos, (double)a.restart * (double)a.restart);
             if (a.restart != (T)0) nz += 1;
-            if (rep) hist_lumped_global<T>(rep, a.hist, win_lo, win_valid, lane == 0 && a.restart != (T)0, a.restart, pred_valid, pred0);
-            else if (a.hist) hist_values<T>(a.hist, win, lane == 0 && a.restart != (T)0, a.restart, pred_valid, pred0);
+            if (a.hist) hist_values<T>(a.hist, win, lane == 0 && a.restart != (T)0, a.restart, pred_valid, pred0);
         }
         __syncwarp();
         // old entries: every kept column has its bit in kbits and its value in oldv
@@ -847,23 +821,17 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T>
     if (a.st->fb_count == 0) {
         // the usual case: no row was deferred, the step's histogram is already complete.  No CTA has row
         // work, so no "last CTA" is needed: CTA 0 scans, the others leave at once.
-        if (a.fused_select && blockIdx.x == 0) {
-            if (a.part) scan_partials<T, WARPS * 32>(a.st, a.part, a.hist);
-            else scan_tail<T, WARPS * 32>(a.st, a.hist);
-        }
+        if (a.fused_select && blockIdx.x == 0) scan_tail<T, WARPS * 32>(a.st, a.hist);
         return;
     }
     for (int i = threadIdx.x; i < kHistWin; i += WARPS * 32) win[i] = 0u;
     __syncthreads();
     dense_rows<T>(a, sc, (long long)blockIdx.x * WARPS + (threadIdx.x >> 5), win);
     __syncthreads();
-    if (a.hist && !a.part) hist_window_flush<T>(a.hist, win);
+    if (a.hist) hist_window_flush<T>(a.hist, win);
 
     // ---- fused select (unsharded walk) when rows were deferred: the histogram is complete only now
-    if (a.fused_select && !a.st->scan_done && last_block(&a.st->tick_dense)) {
-        if (a.part) scan_partials<T, WARPS * 32>(a.st, a.part, a.hist);
-        else scan_tail<T, WARPS * 32>(a.st, a.hist);
-    }
+    if (a.fused_select && !a.st->scan_done && last_block(&a.st->tick_dense)) scan_tail<T, WARPS * 32>(a.st, a.hist);
 }
 
 // Walk state for step 0 (utility.py:275-280), exchange buffer cleared, candidate block header reset.
@@ -874,7 +842,6 @@ __global__ void init_state_kernel(WalkState* st, double rp, double perc, double 
         WalkState s;
         memset(&s, 0, sizeof(s));
         s.rp = rp; s.perc = perc; s.tol = tol; s.max_steps = max_steps;
-        s.prefix_bits = 2 * kSelectBits;
         *st = s;
         cand_block[0] = 0ull;
         cand_block[1] = ~0ull;

@@ -123,97 +123,13 @@ __device__ __noinline__ void scan_level(WalkState* st, const unsigned long long*
     __syncthreads();
 }
 
-// Unsharded walk, after the propagate kernels of a step: folds the kRep partial-sum replicas into the walk
-// state, derives n and the virtual index, and locates the percentile's level-0 bin inside the lumped window
-// (hist_miss if it lies in one of the lumps or no window was set).  When that bin is the one the level-1
-// histogram was pre-filled for, level 1 is scanned straight away.  Called by all BLOCK threads of one CTA.
-template <typename T, int BLOCK>
-__device__ __noinline__ void scan_partials(WalkState* st, const StepPartial* part, unsigned long long* hist) {
-    __shared__ unsigned long long s_bins[kLWin + 2];
-    __shared__ unsigned long long s_tot[5];
-    __shared__ int s_max[2];
-    const int t = threadIdx.x;
-    for (int i = t; i < kLWin + 2 + 5 + 2; i += BLOCK) {
-        if (i < kLWin + 2) {
-            unsigned long long s = 0;
-            for (int r = 0; r < kRep; ++r) s += (unsigned long long)__ldcg(&part[r].win[0] + i);   // win, below, above are contiguous
-            s_bins[i] = s;
-        } else if (i < kLWin + 2 + 5) {
-            const int f = i - (kLWin + 2);
-            unsigned long long s = 0;
-            for (int r = 0; r < kRep; ++r) s += __ldcg(&part[r].sq[0] + f);                         // sq[3], nnz, kept are contiguous
-            s_tot[f] = s;
-        } else {
-            const int f = i - (kLWin + 2 + 5);
-            int mx = 0;
-            for (int r = 0; r < kRep; ++r) { const int v = __ldcg(&part[r].max_kept + f); mx = v > mx ? v : mx; }
-            s_max[f] = mx;
-        }
-    }
-    __syncthreads();
-    if (t == 0) {
-        // rows of the large-row kernel added their share to the walk state directly
-        st->sq_limb[0] += s_tot[0]; st->sq_limb[1] += s_tot[1]; st->sq_limb[2] += s_tot[2];
-        st->nnz_exact += s_tot[3];
-        st->nnz_in += s_tot[4];
-        if (s_max[0] > st->max_kept) st->max_kept = s_max[0];
-        if (s_max[1] > st->max_row_len) st->max_row_len = s_max[1];
-        unsigned long long n = 0;
-        for (int i = 0; i < kLWin + 2; ++i) n += s_bins[i];
-        // numpy percentile(), method 'linear': q and the virtual index live in the data dtype (as scan_level)
-        const T q = div_rn((T)st->perc, (T)100);
-        const T nm1 = (T)(n - 1);
-        const T v = mul_rn(nm1, q);
-        const T kf = floor(v);
-        unsigned long long k = (unsigned long long)kf;
-        int clamp = 0;
-        T g = sub_rn(v, kf);
-        if (v >= nm1 || k >= n - 1) { clamp = 1; k = n - 1; g = (T)0; }
-        st->n_total = n;
-        st->rank_k = k;
-        st->gamma = (double)g;
-        st->clamp_last = clamp;
-        st->below = 0;
-        st->prefix = 0;
-        int miss = st->win_valid ? 0 : 1;
-        if (!miss) {
-            unsigned long long run = s_bins[kLWin];          // the lump under the window
-            int b = -1;
-            if (k >= run) {
-                for (int i = 0; i < kLWin; ++i) {
-                    if (k < run + s_bins[i]) { b = i; break; }
-                    run += s_bins[i];
-                }
-            }
-            if (b < 0) miss = 1;
-            else {
-                st->below = run;
-                st->prefix = (unsigned long long)(st->win_lo + b);
-                st->bin_count = s_bins[b];
-            }
-        }
-        st->hist_miss = miss;
-    }
-    __syncthreads();
-    const bool hit = !st->hist_miss && st->pred_valid && st->prefix == st->pred_prefix0;
-    __syncthreads();
-    if (hit) {
-        scan_level<T, BLOCK>(st, hist, 1);
-        if (t == 0) { st->hist1_ready = 1; st->scan_done = 1; }
-    } else {
-        // level 1 was pre-filled for another bin (or nothing is known): cleared for the pass that follows
-        for (int i = t; i < kSelectBins; i += BLOCK) hist[kSelectBins + i] = 0ull;
-        if (t == 0) { st->hist1_ready = 0; st->scan_done = 1; }
-    }
-}
-
-// Block-wide radix select of local rank r among cand[0..c) (keys share their top prefix_bits bits), 8 bits at
+// Block-wide radix select of local rank r among cand[0..c) (keys share their top 24 bits), 8 bits at
 // a time.  Returns the key, the number of candidates strictly below it and its multiplicity.
 template <int KBITS>
 __device__ void block_radix_select(const unsigned long long* cand, unsigned long long c, unsigned long long r,
                                    unsigned int* sh_hist, unsigned long long* sh_io, unsigned long long& key_out,
-                                   unsigned long long& below_out, unsigned long long& dup_out, int prefix_bits) {
-    int remaining = KBITS - prefix_bits;
+                                   unsigned long long& below_out, unsigned long long& dup_out) {
+    int remaining = KBITS - 2 * kSelectBits;
     unsigned long long known = 0, mask = 0, below = 0, cnt = c;
     while (remaining > 0) {
         const int d = remaining >= 8 ? 8 : remaining;
@@ -245,7 +161,7 @@ __device__ void block_radix_select(const unsigned long long* cand, unsigned long
         remaining = shift;
         __syncthreads();
     }
-    key_out = (cand[0] & ~mask) | known;   // the top prefix_bits bits are common to all candidates
+    key_out = (cand[0] & ~mask) | known;   // the top 24 bits are common to all candidates
     below_out = below;
     dup_out = cnt;
 }
@@ -262,7 +178,6 @@ struct FinishArgs {
     unsigned long long cand_cap;          // keys per block
     crwr_step_record* trace;
     int32_t do_select;                    // 0 on step 0 (utility.py:286)
-    StepPartial* part;                    // unsharded walk: the kRep partial-sum replicas, cleared here (else null)
 };
 
 // Shared-memory scratch the finish step needs (carved from the caller's buffer, 16-byte aligned).
@@ -346,7 +261,7 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
             __syncthreads();
         } else {
             unsigned long long key, below, dup;
-            block_radix_select<KO::bits>(cand, c, r, sh_hist, sh_io, key, below, dup, st->prefix_bits);
+            block_radix_select<KO::bits>(cand, c, r, sh_hist, sh_io, key, below, dup);
             if (r + 1 < below + dup) {
                 if (t == 0) { s_xk = key; s_xk1 = key; s_have1 = 1; }
             } else {
@@ -458,17 +373,9 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
         if (cut_applied) {      // the next cut most likely falls into the same level-0 bin
             st->pred_prefix0 = (unsigned long long)(KO::enc((T)cut) >> (KO::bits - kSelectBits));
             st->pred_valid = 1;
-            int lo = (int)st->pred_prefix0 - kLWin / 2;       // lumped window of the next step, centred on that bin
-            if (lo < 0) lo = 0;
-            if (lo + kLWin > kSelectBins) lo = kSelectBins - kLWin;
-            st->win_lo = lo;
-            st->win_valid = 1;
         } else {
             st->pred_valid = 0;
-            st->win_valid = 0;
         }
-        st->hist_miss = 0;
-        st->prefix_bits = 2 * kSelectBits;
         a.own_block[0] = 0;
         a.own_block[1] = ~0ull;
     }
@@ -479,10 +386,6 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
         for (int i = t; i < (int)(sizeof(WalkState) / 4); i += blockDim.x) dst[i] = src[i];
     }
     for (int i = t; i < kSelectLevels * kSelectBins + kXExtras; i += blockDim.x) a.hist[i] = 0ull;
-    if (a.part) {
-        unsigned int* w = reinterpret_cast<unsigned int*>(a.part);
-        for (int i = t; i < (int)(kRep * sizeof(StepPartial) / 4); i += blockDim.x) w[i] = 0u;
-    }
 }
 
 #undef s_xk
@@ -536,15 +439,8 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const T* vals, WalkSta
     pdl_launch_dependents();
     if (st->done) return;
     if (level == 1 && st->hist1_ready) return;      // the propagate epilogue already filled this level and it was scanned
-    // lumped-window miss (unsharded walk): the percentile's level-0 bin is unknown - this pass counts level 0 in full and
-    // the gather then works from a 12-bit prefix
-    const bool miss = fused_tail && level == 1 && st->hist_miss != 0;
-    const int lv = miss ? 0 : level;
-    hist_pass<T>(vals, (long long)st->cursor, (typename KeyOf<T>::type)st->prefix, lv, sh, hist);
-    if (fused_tail && last_block(&st->tick_hist1)) {
-        scan_level<T, 512>(st, hist, lv);
-        if (threadIdx.x == 0) st->prefix_bits = miss ? kSelectBits : 2 * kSelectBits;
-    }
+    hist_pass<T>(vals, (long long)st->cursor, (typename KeyOf<T>::type)st->prefix, level, sh, hist);
+    if (fused_tail && last_block(&st->tick_hist1)) scan_level<T, 512>(st, hist, level);
 }
 
 template <typename T>
@@ -558,8 +454,7 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(WalkState* st, const 
 // One pass over the value array by the whole grid.
 template <typename T>
 __device__ __forceinline__ void gather_pass(const T* __restrict__ vals, long long n, typename KeyOf<T>::type prefix,
-                                            unsigned long long* block, unsigned long long cand_cap,
-                                            int prefix_bits = 2 * kSelectBits) {
+                                            unsigned long long* block, unsigned long long cand_cap) {
     typedef KeyOf<T> KO;
     typedef typename KO::type K;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -574,7 +469,7 @@ __device__ __forceinline__ void gather_pass(const T* __restrict__ vals, long lon
             const T v = vv[u];
             if (v == (T)0) continue;                  // zero padding of a row reservation (or past the end)
             const K key = KO::enc(v);
-            const K p = key >> (KO::bits - prefix_bits);
+            const K p = key >> (KO::bits - 2 * kSelectBits);
             if (p == prefix) {
                 unsigned long long idx = atomicAdd(&block[0], 1ull);
                 if (idx < cand_cap) block[kCandHeader + idx] = (unsigned long long)key;
@@ -597,7 +492,7 @@ __global__ void __launch_bounds__(512) select_gather_kernel(const T* vals, WalkS
     pdl_wait();
     pdl_launch_dependents();
     if (st->done) return;
-    gather_pass<T>(vals, (long long)st->cursor, (typename KeyOf<T>::type)st->prefix, block, cand_cap, st->prefix_bits);
+    gather_pass<T>(vals, (long long)st->cursor, (typename KeyOf<T>::type)st->prefix, block, cand_cap);
     if (fused && last_block(&st->tick_gather)) finish_step_body<T>(fin, scratch);
 }
 
