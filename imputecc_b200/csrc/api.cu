@@ -17,6 +17,7 @@
 #include "finish.cuh"
 #include "walk.cuh"
 #include "peer.cuh"
+#include "binweights.cuh"
 
 using namespace crwr;
 
@@ -911,6 +912,32 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     h->order_valid = false;
     h->walking = true;
     h->mode = h->mode_next;
+    return CRWR_OK;
+}
+
+int32_t crwr_bin_contact_weights(int32_t dtype, int64_t m, const int64_t* d_indptr, const int32_t* d_indices, const void* d_data,
+                                 int64_t n_rows, const int32_t* d_rows, int64_t n_bins, const int64_t* d_bin_ptr,
+                                 const int32_t* d_bin_members, void* d_out, void* stream) {
+    if (dtype != CRWR_F32 && dtype != CRWR_F64) CRWR_FAIL(CRWR_ERR_INVALID, "dtype must be CRWR_F32 or CRWR_F64");
+    if (m < 1 || n_rows < 0 || n_bins < 0) CRWR_FAIL(CRWR_ERR_INVALID, "bad sizes");
+    if (n_rows == 0 || n_bins == 0) return CRWR_OK;
+    if (!d_indptr || !d_indices || !d_data || !d_rows || !d_bin_ptr || !d_bin_members || !d_out)
+        CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) CRWR_FAIL(CRWR_ERR_CUDA, "no CUDA device: libcrwr_b200 has no CPU path");
+    const long long total = (long long)n_rows * n_bins;
+    const int tb = 256;
+    const long long grid = (total + tb - 1) / tb;
+    if (grid > 2147483647ll) CRWR_FAIL(CRWR_ERR_INVALID, "too many (contig, bin) pairs for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CRWR_F64)
+        bin_weights_kernel<double><<<(int)grid, tb, 0, st>>>(d_indptr, d_indices, (const double*)d_data, d_rows, n_rows, d_bin_ptr,
+                                                             d_bin_members, n_bins, (double*)d_out);
+    else
+        bin_weights_kernel<float><<<(int)grid, tb, 0, st>>>(d_indptr, d_indices, (const float*)d_data, d_rows, n_rows, d_bin_ptr,
+                                                            d_bin_members, n_bins, (float*)d_out);
+    LAUNCH_CHECK();
     return CRWR_OK;
 }
 

@@ -15,6 +15,8 @@
  *                                                         (per-phase calls for the sharded walk)
  *   Script/utility.py:306-307     Q[:m,:m]                crwr_result_count / crwr_result_write
  *   Script/imputation.py:122-127  E=Q+Q^T, D^-1/2 E D^-1/2 crwr_symmetrise_count / _write
+ *   Script/utility.py:466-480     match_contigs edge       crwr_bin_contact_weights
+ *                                 weights (next row, 8f)
  *
  * Conventions
  *   - every pointer named d_* is a DEVICE pointer (e.g. torch.Tensor.data_ptr()); h_* is host.
@@ -198,6 +200,15 @@ int32_t crwr_symmetrise_count(int32_t dtype, int64_t m, const int64_t* d_indptr,
 int32_t crwr_symmetrise_write(int32_t dtype, int64_t m, const int64_t* d_indptr, const int32_t* d_indices,
                               const void* d_data, int64_t nnz, void* d_scratch, int64_t scratch_bytes,
                               int64_t* d_out_indptr, int32_t* d_out_indices, void* d_out_data, void* stream);
+
+/* utility.py:466-480 (match_contigs, edge weights of one iteration): for every contig to bin
+ * d_rows[r] and every bin b (members d_bin_members[d_bin_ptr[b] .. d_bin_ptr[b+1]) in the order of the reference's
+ * bin list, never empty), out[r * n_bins + b] = -(sum over the members j of E[row, j]) / size(b), summed in that
+ * order in the matrix dtype.  E: m x m CSR with sorted rows (the output of crwr_symmetrise_write), local contig
+ * indices throughout.  Stateless; only enqueues one kernel. */
+int32_t crwr_bin_contact_weights(int32_t dtype, int64_t m, const int64_t* d_indptr, const int32_t* d_indices, const void* d_data,
+                                 int64_t n_rows, const int32_t* d_rows, int64_t n_bins, const int64_t* d_bin_ptr,
+                                 const int32_t* d_bin_members, void* d_out, void* stream);
 
 /* Measurement aid: with profiling enabled every launch of the propagation kernel (the dominant
  * kernel) is bracketed by CUDA events on the launching stream; read returns the summed duration of
