@@ -6,9 +6,9 @@ match_contigs (binning.py).
 from .crwr import (DEFAULT_MAX_STEPS, DEFAULT_TOL, Walker, WalkInfo, crwr_impute, imputation_b200, install,
                    markers_first_order, random_walk_b200, shard_rows, stack_row_blocks, symmetrise_normalise,
                    validate_inputs)
-from .binning import bin_contact_weights, bins_to_arrays
+from .binning import BinContactWeights, bin_contact_weights, bins_to_arrays
 
 __all__ = ["Walker", "WalkInfo", "crwr_impute", "random_walk_b200", "imputation_b200", "install",
            "symmetrise_normalise", "markers_first_order", "shard_rows", "stack_row_blocks", "validate_inputs",
-           "DEFAULT_TOL", "DEFAULT_MAX_STEPS", "bin_contact_weights", "bins_to_arrays"]
+           "DEFAULT_TOL", "DEFAULT_MAX_STEPS", "BinContactWeights", "bin_contact_weights", "bins_to_arrays"]
 __version__ = "0.1.0"

@@ -32,49 +32,67 @@ def bins_to_arrays(bins, index_of=None):
     return ptr, members
 
 
+class BinContactWeights:
+    """The imputed matrix kept on the GPU for the ~100 iterations of one ``match_contigs`` call: upload once, then one
+    small launch per iteration.  ``weights(to_bin, bin_ptr, bin_members)`` as :func:`bin_contact_weights`."""
+
+    def __init__(self, E, device=None):
+        torch = _torch()
+        self.device = _require_cuda(device)
+        E = sp.csr_matrix(E)
+        if E.shape[0] != E.shape[1]:
+            raise ValueError("E must be square")
+        if E.dtype not in (np.float32, np.float64):
+            raise ValueError("E must be float32 or float64")
+        if not E.has_sorted_indices:
+            E = E.copy()
+            E.sort_indices()
+        self.m = E.shape[0]
+        self.np_dtype = E.dtype
+        self.code = CRWR_F64 if E.dtype == np.float64 else CRWR_F32
+        self.lib = _lib.load()
+        with torch.cuda.device(self.device):
+            self.d_ip = self._up(E.indptr.astype(np.int64, copy=False))
+            self.d_ix = self._up(E.indices.astype(np.int32, copy=False) if E.nnz else np.zeros(1, np.int32))
+            self.d_dt = self._up(E.data if E.nnz else np.zeros(1, E.dtype))
+
+    def _up(self, a):
+        return _torch().from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=True)
+
+    def weights(self, to_bin, bin_ptr, bin_members) -> np.ndarray:
+        torch = _torch()
+        m = self.m
+        to_bin = np.ascontiguousarray(to_bin, dtype=np.int32)
+        bin_ptr = np.ascontiguousarray(bin_ptr, dtype=np.int64)
+        bin_members = np.ascontiguousarray(bin_members, dtype=np.int32)
+        n_bins = bin_ptr.size - 1
+        if n_bins < 0 or (bin_ptr.size and bin_ptr[0] != 0) or (n_bins >= 0 and bin_ptr[-1] != bin_members.size):
+            raise ValueError("bin_ptr must start at 0 and end at len(bin_members)")
+        if n_bins > 0 and np.any(np.diff(bin_ptr) <= 0):
+            raise ValueError("every bin must hold at least one contig")
+        for name, arr in (("to_bin", to_bin), ("bin_members", bin_members)):
+            if arr.size and (arr.min() < 0 or arr.max() >= m):
+                raise ValueError("%s holds an index outside [0, %d)" % (name, m))
+        out_shape = (to_bin.size, max(n_bins, 0))
+        if to_bin.size == 0 or n_bins <= 0:
+            return np.zeros(out_shape, dtype=self.np_dtype)
+        with torch.cuda.device(self.device):
+            d_rows, d_ptr, d_mem = self._up(to_bin), self._up(bin_ptr), self._up(bin_members)
+            d_out = torch.empty(out_shape, dtype=torch.float64 if self.code == CRWR_F64 else torch.float32, device=self.device)
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.lib.crwr_bin_contact_weights(self.code, m, C.c_void_p(self.d_ip.data_ptr()),
+                                                         C.c_void_p(self.d_ix.data_ptr()), C.c_void_p(self.d_dt.data_ptr()),
+                                                         to_bin.size, C.c_void_p(d_rows.data_ptr()), n_bins,
+                                                         C.c_void_p(d_ptr.data_ptr()), C.c_void_p(d_mem.data_ptr()),
+                                                         C.c_void_p(d_out.data_ptr()), stream))
+            return d_out.cpu().numpy()
+
+
 def bin_contact_weights(E, to_bin, bin_ptr, bin_members, device=None) -> np.ndarray:
     """weights[r, b] = -(sum_j E[to_bin[r], members_b[j]]) / len(members_b), utility.py:466-480.
 
     ``E``: imputed m x m scipy matrix (float32 as the reference's, or float64); ``to_bin``: local contig indices;
     ``bin_ptr`` / ``bin_members``: the bins in CSR form (see :func:`bins_to_arrays`), every bin non-empty.
-    Returns a ``(len(to_bin), n_bins)`` array of E's dtype.
+    Returns a ``(len(to_bin), n_bins)`` array of E's dtype.  One-shot form of :class:`BinContactWeights`.
     """
-    torch = _torch()
-    device = _require_cuda(device)
-    E = sp.csr_matrix(E)
-    if E.shape[0] != E.shape[1]:
-        raise ValueError("E must be square")
-    if E.dtype not in (np.float32, np.float64):
-        raise ValueError("E must be float32 or float64")
-    if not E.has_sorted_indices:
-        E = E.copy()
-        E.sort_indices()
-    m = E.shape[0]
-    to_bin = np.ascontiguousarray(to_bin, dtype=np.int32)
-    bin_ptr = np.ascontiguousarray(bin_ptr, dtype=np.int64)
-    bin_members = np.ascontiguousarray(bin_members, dtype=np.int32)
-    n_bins = bin_ptr.size - 1
-    if n_bins < 0 or (bin_ptr.size and bin_ptr[0] != 0) or (n_bins >= 0 and bin_ptr[-1] != bin_members.size):
-        raise ValueError("bin_ptr must start at 0 and end at len(bin_members)")
-    if n_bins > 0 and np.any(np.diff(bin_ptr) <= 0):
-        raise ValueError("every bin must hold at least one contig")
-    for name, arr in (("to_bin", to_bin), ("bin_members", bin_members)):
-        if arr.size and (arr.min() < 0 or arr.max() >= m):
-            raise ValueError("%s holds an index outside [0, %d)" % (name, m))
-    out_shape = (to_bin.size, max(n_bins, 0))
-    if to_bin.size == 0 or n_bins <= 0:
-        return np.zeros(out_shape, dtype=E.dtype)
-    lib = _lib.load()
-    code = CRWR_F64 if E.dtype == np.float64 else CRWR_F32
-    with torch.cuda.device(device):
-        def up(a):
-            return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
-        d_ip, d_ix, d_dt = up(E.indptr.astype(np.int64, copy=False)), up(E.indices.astype(np.int32, copy=False)), up(E.data)
-        d_rows, d_ptr, d_mem = up(to_bin), up(bin_ptr), up(bin_members if bin_members.size else np.zeros(1, np.int32))
-        d_out = torch.empty(out_shape, dtype=torch.float64 if code == CRWR_F64 else torch.float32, device=device)
-        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        _lib.check(lib.crwr_bin_contact_weights(code, m, C.c_void_p(d_ip.data_ptr()), C.c_void_p(d_ix.data_ptr()),
-                                                C.c_void_p(d_dt.data_ptr()), to_bin.size, C.c_void_p(d_rows.data_ptr()), n_bins,
-                                                C.c_void_p(d_ptr.data_ptr()), C.c_void_p(d_mem.data_ptr()),
-                                                C.c_void_p(d_out.data_ptr()), stream))
-        return d_out.cpu().numpy()
+    return BinContactWeights(E, device).weights(to_bin, bin_ptr, bin_members)

@@ -38,6 +38,12 @@ def test_oracle_matches_reference_vectors(name):
     assert np.array_equal(bits(loops.astype(np.float32)), bits(rec["weights"]))
 
 
+def test_bins_to_arrays_follows_bin_index_and_list_order():
+    from imputecc_b200 import bins_to_arrays
+    ptr, mem = bins_to_arrays({2: ["c", "a"], 0: ["b"]}, {"a": 0, "b": 1, "c": 2})
+    assert ptr.tolist() == [0, 1, 3] and mem.tolist() == [1, 2, 0]
+
+
 def test_empty_contact_gives_negative_zero():
     E = sp.csr_matrix((4, 4), dtype=np.float32)
     got = bw.bin_contact_weights(E, np.array([3]), np.array([0, 2, 3]), np.array([0, 1, 2], dtype=np.int32))
@@ -49,9 +55,12 @@ def test_empty_contact_gives_negative_zero():
 def test_gpu_matches_reference_vectors(cuda_device, name):
     import imputecc_b200 as pkg
     E, recs = load(name)
+    resident = pkg.BinContactWeights(E, device=cuda_device)          # the matrix stays on the GPU across iterations
     for rec in recs:
         got = pkg.bin_contact_weights(E, rec["to_bin"], rec["bin_ptr"], rec["bin_members"], device=cuda_device)
         assert got.dtype == np.float32 and np.array_equal(bits(got), bits(rec["weights"]))
+        again = resident.weights(rec["to_bin"], rec["bin_ptr"], rec["bin_members"])
+        assert np.array_equal(bits(again), bits(rec["weights"]))
 
 
 @pytest.mark.gpu
