@@ -307,6 +307,12 @@ int configure_group_shape(crwr_handle_s* h, long long max_row_len, long long max
     const int wmax = 4;
     int wfix = 0;
     if (const char* e = getenv("CRWR_GROUP_WARPS")) { const int g = atoi(e); if (g >= 1 && g <= 8) wfix = g; }
+    // overflow list entries = expected longest row / ov_div.  Long rows fill their table to the nominal load more
+    // often and spill several products per overflowing column: a quarter instead of an eighth removes the large-row
+    // fallbacks of c4_dense (24 -> 1 rows per walk, -10 % per step); short rows keep the smaller list (it would cost
+    // them a CTA per SM).
+    long long ov_div = want > 512 ? 4 : 8;
+    if (const char* e = getenv("CRWR_GROUP_OV_DIV")) { const int v = atoi(e); if (v >= 1 && v <= 64) ov_div = v; }
     // table, kept list and CTA size for one table load
     auto make = [&](int load_pct, long long* in_flight) -> GroupShape {
         GroupShape sh;
@@ -316,7 +322,7 @@ int configure_group_shape(crwr_handle_s* h, long long max_row_len, long long max
             if (H > 65520) { H = 65520; w_ = H * load_pct / 100; }
             if (km > H) km = H;
             sh.H = (int)H; sh.limit = (int)round_up(w_, 8); sh.kmax = (int)km;
-            sh.ov_cap = (int)(w_ / 8 < 16 ? 16 : (w_ / 8 > 256 ? 256 : round_up(w_ / 8, 8)));
+            sh.ov_cap = (int)(w_ / ov_div < 16 ? 16 : (w_ / ov_div > 512 ? 512 : round_up(w_ / ov_div, 8)));
             sh.per_row = group_smem_per_row<T>(sh.H, sh.limit, sh.kmax, sh.ov_cap);
             if (sh.per_row <= budget) break;
             // too big for one SM: shrink (oversized rows are deferred to the large-row kernel)
