@@ -12,7 +12,7 @@ walk steps executed per second of walk time.
          (crwr_walk_init .. stop rule), CUDA events on the launching stream, max over ranks.
   e2e    the same metric through the public call crwr_impute() with HOST buffers: pinned
          NormCC CSR in, scipy matrix out, copies inside the timed region.
-  roofline  the dominant kernel (propagate_kernel): algorithmic bytes per launch / its mean
+  roofline  the dominant kernel (propagate_group_kernel; propagate_kernel for step 0): algorithmic bytes per launch / its mean
          duration measured live with CUDA events, against MEASURED_PEAKS.json hbm_gbs.
 
 N > 1 (torchrun): weak scaling - every rank walks 8,000 restart rows of a problem N times larger
