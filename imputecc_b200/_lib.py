@@ -84,7 +84,9 @@ _SIGNATURES = {
     "crwr_symmetrise_count": (C.c_int32, [C.c_int32, C.c_int64, _P, _P, _P, C.c_int64, _P, C.c_int64,
                                           C.POINTER(C.c_int64), _P]),
     "crwr_symmetrise_write": (C.c_int32, [C.c_int32, C.c_int64, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
-    "crwr_bin_contact_weights": (C.c_int32, [C.c_int32, C.c_int64, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
+    "crwr_bin_contact_scratch_bytes": (C.c_int64, [C.c_int64]),
+    "crwr_bin_contact_weights": (C.c_int32, [C.c_int32, C.c_int64, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, _P,
+                                             C.c_int64, _P, _P]),
 }
 
 _lib = None

@@ -55,6 +55,8 @@ class BinContactWeights:
             self.d_ip = self._up(E.indptr.astype(np.int64, copy=False))
             self.d_ix = self._up(E.indices.astype(np.int32, copy=False) if E.nnz else np.zeros(1, np.int32))
             self.d_dt = self._up(E.data if E.nnz else np.zeros(1, E.dtype))
+            self.scratch_bytes = int(self.lib.crwr_bin_contact_scratch_bytes(self.m))
+            self.d_scratch = torch.empty(self.scratch_bytes, dtype=torch.uint8, device=self.device)   # inverse map of the bins
 
     def _up(self, a):
         return _torch().from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=True)
@@ -73,6 +75,7 @@ class BinContactWeights:
         for name, arr in (("to_bin", to_bin), ("bin_members", bin_members)):
             if arr.size and (arr.min() < 0 or arr.max() >= m):
                 raise ValueError("%s holds an index outside [0, %d)" % (name, m))
+        disjoint = int(np.bincount(bin_members, minlength=1).max()) <= 1      # as in the reference: a contig sits in one bin
         out_shape = (to_bin.size, max(n_bins, 0))
         if to_bin.size == 0 or n_bins <= 0:
             return np.zeros(out_shape, dtype=self.np_dtype)
@@ -83,7 +86,9 @@ class BinContactWeights:
             _lib.check(self.lib.crwr_bin_contact_weights(self.code, m, C.c_void_p(self.d_ip.data_ptr()),
                                                          C.c_void_p(self.d_ix.data_ptr()), C.c_void_p(self.d_dt.data_ptr()),
                                                          to_bin.size, C.c_void_p(d_rows.data_ptr()), n_bins,
-                                                         C.c_void_p(d_ptr.data_ptr()), C.c_void_p(d_mem.data_ptr()),
+                                                         C.c_void_p(d_ptr.data_ptr()), C.c_void_p(d_mem.data_ptr()), bin_members.size,
+                                                         C.c_void_p(self.d_scratch.data_ptr()) if disjoint else None,
+                                                         self.scratch_bytes if disjoint else 0,
                                                          C.c_void_p(d_out.data_ptr()), stream))
             return d_out.cpu().numpy()
 

@@ -921,22 +921,48 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     return CRWR_OK;
 }
 
+int64_t crwr_bin_contact_scratch_bytes(int64_t m) { return m < 1 ? -1 : 8 * m; }
+
 int32_t crwr_bin_contact_weights(int32_t dtype, int64_t m, const int64_t* d_indptr, const int32_t* d_indices, const void* d_data,
                                  int64_t n_rows, const int32_t* d_rows, int64_t n_bins, const int64_t* d_bin_ptr,
-                                 const int32_t* d_bin_members, void* d_out, void* stream) {
+                                 const int32_t* d_bin_members, int64_t n_members, void* d_scratch, int64_t scratch_bytes,
+                                 void* d_out, void* stream) {
     if (dtype != CRWR_F32 && dtype != CRWR_F64) CRWR_FAIL(CRWR_ERR_INVALID, "dtype must be CRWR_F32 or CRWR_F64");
-    if (m < 1 || n_rows < 0 || n_bins < 0) CRWR_FAIL(CRWR_ERR_INVALID, "bad sizes");
+    if (m < 1 || n_rows < 0 || n_bins < 0 || n_members < 0) CRWR_FAIL(CRWR_ERR_INVALID, "bad sizes");
     if (n_rows == 0 || n_bins == 0) return CRWR_OK;
     if (!d_indptr || !d_indices || !d_data || !d_rows || !d_bin_ptr || !d_bin_members || !d_out)
         CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
+    if (d_scratch && scratch_bytes < 8 * m) CRWR_FAIL(CRWR_ERR_INVALID, "scratch too small: need %lld bytes", (long long)(8 * m));
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (ndev < 1) CRWR_FAIL(CRWR_ERR_CUDA, "no CUDA device: libcrwr_b200 has no CPU path");
-    const long long total = (long long)n_rows * n_bins;
+    cudaStream_t st = (cudaStream_t)stream;
     const int tb = 256;
+    if (d_scratch) {
+        // work proportional to the stored entries of the rows: inverse map of the bins, then one warp per contig
+        int32_t* bin_of = (int32_t*)d_scratch;
+        int32_t* pos_of = bin_of + m;
+        CUDA_TRY(cudaMemsetAsync(bin_of, 0xff, 4 * (size_t)m, st));
+        if (n_members > 0) {
+            bin_inverse_kernel<<<(int)((n_members + tb - 1) / tb), tb, 0, st>>>(d_bin_ptr, d_bin_members, n_bins, bin_of, pos_of);
+            LAUNCH_CHECK();
+        }
+        const long long grid = (n_rows + kBinRowWarps - 1) / kBinRowWarps;
+        if (grid > 2147483647ll) CRWR_FAIL(CRWR_ERR_INVALID, "too many contigs for one launch");
+        if (dtype == CRWR_F64)
+            bin_weights_rows_kernel<double><<<(int)grid, kBinRowWarps * 32, 0, st>>>(d_indptr, d_indices, (const double*)d_data, d_rows,
+                                                                                   n_rows, d_bin_ptr, d_bin_members, n_bins, bin_of,
+                                                                                   pos_of, (double*)d_out);
+        else
+            bin_weights_rows_kernel<float><<<(int)grid, kBinRowWarps * 32, 0, st>>>(d_indptr, d_indices, (const float*)d_data, d_rows,
+                                                                                  n_rows, d_bin_ptr, d_bin_members, n_bins, bin_of,
+                                                                                  pos_of, (float*)d_out);
+        LAUNCH_CHECK();
+        return CRWR_OK;
+    }
+    const long long total = (long long)n_rows * n_bins;
     const long long grid = (total + tb - 1) / tb;
     if (grid > 2147483647ll) CRWR_FAIL(CRWR_ERR_INVALID, "too many (contig, bin) pairs for one launch");
-    cudaStream_t st = (cudaStream_t)stream;
     if (dtype == CRWR_F64)
         bin_weights_kernel<double><<<(int)grid, tb, 0, st>>>(d_indptr, d_indices, (const double*)d_data, d_rows, n_rows, d_bin_ptr,
                                                              d_bin_members, n_bins, (double*)d_out);

@@ -203,12 +203,16 @@ int32_t crwr_symmetrise_write(int32_t dtype, int64_t m, const int64_t* d_indptr,
 
 /* utility.py:466-480 (match_contigs, edge weights of one iteration): for every contig to bin
  * d_rows[r] and every bin b (members d_bin_members[d_bin_ptr[b] .. d_bin_ptr[b+1]) in the order of the reference's
- * bin list, never empty), out[r * n_bins + b] = -(sum over the members j of E[row, j]) / size(b), summed in that
- * order in the matrix dtype.  E: m x m CSR with sorted rows (the output of crwr_symmetrise_write), local contig
- * indices throughout.  Stateless; only enqueues one kernel. */
+ * bin list, never empty, bins disjoint), out[r * n_bins + b] = -(sum over the members j of E[row, j]) / size(b), summed
+ * in that order in the matrix dtype.  E: m x m CSR with sorted rows (the output of crwr_symmetrise_write), local contig
+ * indices throughout; n_members = d_bin_ptr[n_bins].  d_scratch: crwr_bin_contact_scratch_bytes(m) bytes for the
+ * inverse map of the bins (work then proportional to the stored entries of the rows), or NULL (one thread per
+ * (contig, bin) pair with binary searches; bins may then overlap).  Stateless; only enqueues kernels. */
+int64_t crwr_bin_contact_scratch_bytes(int64_t m);
 int32_t crwr_bin_contact_weights(int32_t dtype, int64_t m, const int64_t* d_indptr, const int32_t* d_indices, const void* d_data,
                                  int64_t n_rows, const int32_t* d_rows, int64_t n_bins, const int64_t* d_bin_ptr,
-                                 const int32_t* d_bin_members, void* d_out, void* stream);
+                                 const int32_t* d_bin_members, int64_t n_members, void* d_scratch, int64_t scratch_bytes,
+                                 void* d_out, void* stream);
 
 /* Measurement aid: with profiling enabled every launch of the propagation kernel (the dominant
  * kernel) is bracketed by CUDA events on the launching stream; read returns the summed duration of

@@ -82,6 +82,28 @@ def test_gpu_matches_oracle_on_random_bins(cuda_device, dtype):
 
 
 @pytest.mark.gpu
+def test_gpu_long_rows_and_overlapping_bins(cuda_device):
+    """Rows longer than the shared-memory list take the binary-search form inside the row kernel; bins that share a
+    contig (never produced by the reference, but legal input) take the pair kernel."""
+    import imputecc_b200 as pkg
+    rng = np.random.default_rng(9)
+    m = 1500
+    E = sp.random(m, m, density=0.25, format="csr", dtype=np.float32, random_state=3)     # ~375 stored entries per row
+    E.sort_indices()
+    assert np.diff(E.indptr).max() > 256
+    perm = rng.permutation(m)
+    to_bin = np.sort(perm[:64]).astype(np.int32)
+    rest = perm[64:1200].astype(np.int32)
+    bin_ptr = np.arange(0, rest.size + 1, 8, dtype=np.int64)
+    got = pkg.bin_contact_weights(E, to_bin, bin_ptr, rest, device=cuda_device)
+    assert np.array_equal(bits(got), bits(bw.bin_contact_weights(E, to_bin, bin_ptr, rest)))
+    overlapping = np.concatenate([rest[:40], rest[:40]])                                  # every contig in two bins
+    ptr2 = np.arange(0, overlapping.size + 1, 10, dtype=np.int64)
+    got = pkg.bin_contact_weights(E, to_bin, ptr2, overlapping, device=cuda_device)
+    assert np.array_equal(bits(got), bits(bw.bin_contact_weights(E, to_bin, ptr2, overlapping)))
+
+
+@pytest.mark.gpu
 def test_gpu_argument_errors(cuda_device):
     import imputecc_b200 as pkg
     E = sp.identity(5, dtype=np.float32, format="csr")
