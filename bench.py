@@ -15,9 +15,11 @@ walk steps executed per second of walk time.
   roofline  the dominant kernel (propagate_group_kernel; propagate_kernel for step 0): algorithmic bytes per launch / its mean
          duration measured live with CUDA events, against MEASURED_PEAKS.json hbm_gbs.
 
-N > 1 (torchrun): weak scaling - every rank walks 8,000 restart rows of a problem N times larger
-(8,000 N markers on 50,000 N contigs, the m/N ratio of BASELINE configs 2-4); value is scaled by
-m/8000 so that it stays a whole-job aggregate.
+N > 1 (torchrun): STRONG scaling of the same named workload (BASELINE config 3: 8,000 markers at 1/2/4/8
+GPUs; `--workload c4_sparse --gpus 8` is config 4): the restart rows are sharded over the ranks, the
+transition matrix is replicated, metric and unit stay "walk-steps/s" of the whole job.  Every line carries
+`result_sha256` of the imputed matrix (canonical CSR: indptr | indices | data), so equal hashes at N = 1, 2, 4, 8
+are the multi-GPU parity proof.
 """
 from __future__ import annotations
 
@@ -34,16 +36,23 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-BLOCK_MARKERS = 8000
-
-
 def workload_for(name: str, world: int):
+    """The named workload, whatever the number of GPUs (strong scaling)."""
     from imputecc_b200 import synth
-    base = synth.WORKLOADS[name]
-    if world == 1:
-        return base
-    return synth.Workload("%s_x%d" % (base.name, world), base.n_contigs * world, base.n_markers * world,
-                          base.genome_size, base.intra_degree, base.inter_degree, base.matrix_seed, base.marker_seed)
+    return synth.WORKLOADS[name]
+
+
+def result_sha256(E) -> str:
+    """sha256 of the canonical CSR form of the imputed matrix (int64 indptr | int32 indices | data)."""
+    import hashlib
+    import scipy.sparse as sp
+    E = sp.csr_matrix(E).copy()
+    E.sort_indices()
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(E.indptr.astype(np.int64)).tobytes())
+    h.update(np.ascontiguousarray(E.indices.astype(np.int32)).tobytes())
+    h.update(np.ascontiguousarray(E.data).tobytes())
+    return h.hexdigest()
 
 
 def walk_bytes(trace, nnz_p, n, s):
@@ -133,8 +142,27 @@ def pinned_csr(M):
 
 
 # ---------------------------------------------------------------------------------------------
+def _reference_walk():
+    """The unmodified reference walk (Script.utility.random_walk_cpu) when the reference tree is importable
+    (build container: /root/reference; a copy under baseline/_ref would do as well); None on the GPU box."""
+    for root in ("/root/reference", os.path.join(REPO, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(root, "Script")):
+            try:
+                if root not in sys.path:
+                    sys.path.insert(0, root)
+                import logging
+                logging.disable(logging.CRITICAL)
+                from Script.utility import random_walk_cpu
+                return random_walk_cpu, root
+            except Exception:
+                continue
+    return None, None
+
+
 def run_reference(args, rank, world):
-    """The reference's own algorithm (scipy / numpy, single-threaded like the reference) on the host."""
+    """The reference's CPU implementation of the path on the host (scipy / numpy are single-threaded here, as in
+    the reference): the unmodified `random_walk_cpu` when the reference tree is importable, else the oracle port
+    (bit-pinned to it, tests/test_oracle.py).  Pre/post steps (imputation.py:112-119, :122-127) are timed beside."""
     if rank != 0:
         return
     from imputecc_b200 import synth
@@ -142,28 +170,49 @@ def run_reference(args, rank, world):
     wl = workload_for(args.workload, 1)
     M, idx = synth.make_workload(wl)
     np_dtype = np.float32               # the reference casts P to float32 (imputation.py:119)
+    t0 = time.perf_counter()
     perm = oracle.marker_permutation(M.shape[0], idx)
     P = oracle.transition_matrix(M, perm, np_dtype)
+    pre_s = time.perf_counter() - t0
     max_steps = args.ref_walk_steps
-    times, steps = [], 0
+    ref_walk, ref_root = _reference_walk()
+    kind = "reference" if (ref_walk is not None and max_steps >= 500) else "port"
+    times, steps, post_s = [], 0, 0.0
     for i in range(args.warmup + args.steps):
         tr = oracle.WalkTrace()
-        t0 = time.perf_counter()
-        oracle.crwr_walk(P, 0.5, 80, 0.01, idx.size, max_steps=max_steps, trace=tr)
-        dt = time.perf_counter() - t0
+        if kind == "reference":
+            t0 = time.perf_counter()
+            Q = ref_walk(P, 0.5, 80, 0.01, idx.size)
+            dt = time.perf_counter() - t0
+            if not steps or i == 0:
+                oracle.crwr_walk(P, 0.5, 80, 0.01, idx.size, trace=tr)       # step count of the identical walk (untimed)
+                n_steps = len(tr.steps)
+        else:
+            t0 = time.perf_counter()
+            Q = oracle.crwr_walk(P, 0.5, 80, 0.01, idx.size, max_steps=max_steps, trace=tr)
+            dt = time.perf_counter() - t0
+            n_steps = len(tr.steps)
         if i >= args.warmup:
             times.append(dt)
-            steps += len(tr.steps)
+            steps += n_steps
+            t0 = time.perf_counter()
+            E = oracle.symmetrise_normalise(Q)
+            post_s = time.perf_counter() - t0
     total = sum(times)
     value = steps / total
     sample = "full walk" if max_steps >= 500 else "first %d walk steps of each walk" % max_steps
     line = {"impl": "reference", "metric": "crwr_walk_steps_per_s", "value": value, "unit": "walk-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(wl, 1, "f32"),
-            "cpu_baseline": {"value": value, "unit": "walk-steps/s", "cores": 1, "kind": "port",
-                             "sample": "%s; scipy.sparse + np.percentile are serial, 1 of %d host cores used" %
-                                       (sample, os.cpu_count())},
+            "cpu_baseline": {"value": value, "unit": "walk-steps/s", "cores": 1, "kind": kind,
+                             "sample": "%s (%s); scipy.sparse + np.percentile are serial, 1 of %d host cores used" %
+                                       (sample, "unmodified Script.utility.random_walk_cpu from %s" % ref_root if kind == "reference"
+                                        else "oracle port, same scipy calls", os.cpu_count())},
+            "pre_post_s": {"transition_matrix_s": pre_s, "symmetrise_normalise_s": post_s,
+                           "note": "imputation.py:112-119 and :122-127 restated (oracle), outside the walk metric; the O(N^2) "
+                                   "permutation-list loop of imputation.py:108-110 is not included"},
+            "result_sha256": result_sha256(E),
             "e2e": {"value": value, "unit": "walk-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -225,6 +274,7 @@ def main():
 
     use_peer = world > 1 and sharded.peer_exchange_available(dist, dist.group.WORLD)
     peer = sharded.PeerExchange.get(dist, dist.group.WORLD, device) if use_peer else None
+    use_peer = peer is not None
 
     def one_walk():
         if world == 1:
@@ -265,10 +315,7 @@ def main():
         print("trace:", [(t["nnz_in"], t["nnz_new"], t["max_row_len"], t["max_kept"], t["fallback_rows"]) for t in trace], file=sys.stderr)
 
     # ---- dominant kernel, live (CUDA events inside the library on the launching stream) ----
-    # pass A, default execution mode: with small rows the whole chunk of steps is ONE persistent kernel
-    # (walk_chunk_kernel) and the events bracket each of its launches; otherwise they bracket propagate_kernel.
-    def profiled_walk(mode):
-        walker.set_mode(mode)
+    def profiled_walk():
         lib.crwr_profile(walker.handle, 1)
         flush.fill_(1)
         one_walk()
@@ -280,21 +327,10 @@ def main():
         return ms.value, int(nl.value), list(ph)
 
     steps_per_walk = len(trace)
-    if world == 1:
-        default_mode = int(os.environ.get("CRWR_WALK_MODE", "0"))
-        kern_ms, kern_launches, _ = profiled_walk(default_mode)
-        prop_ms, _, phases = profiled_walk(0)          # one launch per phase -> propagate_kernel alone
-        walker.set_mode(default_mode)
-        persistent = kern_launches < steps_per_walk     # fewer launches than steps: chunks ran as one kernel each
-    else:
-        lib.crwr_profile(walker.handle, 1)
-        flush.fill_(1)
-        one_walk()
-        ms, nl = _lib.C.c_double(0), _lib.C.c_int64(0)
-        _lib.check(lib.crwr_profile_read(walker.handle, _lib.C.byref(ms), _lib.C.byref(nl), walker._stream()))
-        lib.crwr_profile(walker.handle, 0)
-        kern_ms = prop_ms = ms.value
-        kern_launches, phases, persistent = int(nl.value), [0.0, 0.0, 0.0], False
+    prop_ms, kern_launches, phases = profiled_walk()
+    kern_ms = prop_ms
+    if world > 1:
+        phases = [0.0, 0.0, 0.0]
     prop_ms_per_launch = prop_ms / max(steps_per_walk, 1)       # launches after the stop are no-ops (~0 ms)
 
     # ---- end to end through the public API, host buffers --------------------------------------
@@ -321,9 +357,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     walk_ms, e2e_ms = float(t[0]), float(t[1])
 
-    scale = m / BLOCK_MARKERS if world > 1 else 1.0
-    value = scale * walk_steps / (walk_ms * 1e-3)
-    e2e_value = scale * e2e_steps / (e2e_ms * 1e-3)
+    value = walk_steps / (walk_ms * 1e-3)
+    e2e_value = e2e_steps / (e2e_ms * 1e-3)
     total_bytes, prop_bytes = walk_bytes(trace, nnz_p, n, s)
     peak, peak_src = measured_hbm_peak()
     # rows are sharded: this rank's propagate launch moves ~1/world of the iterate plus all of W
@@ -334,22 +369,15 @@ def main():
     prop_achieved = prop_bytes_launch / (prop_ms_per_launch * 1e-3) / 1e9 if prop_ms_per_launch > 0 else 0.0
     step_ms = walk_ms / max(walk_steps, 1)
     step_gbs = (total_bytes / max(steps_per_walk, 1)) / (step_ms * 1e-3) / 1e9
-    if persistent:
-        # the dominant kernel is the persistent walk kernel: one launch = a chunk of whole walk steps
-        dom_name = "walk_chunk_kernel (persistent cooperative kernel: all phases of a chunk of walk steps)"
-        dom_bytes = total_bytes / max(kern_launches, 1)
-        dom_us = 1e3 * kern_ms / max(kern_launches, 1)
-        achieved = total_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
-    else:
-        dom_name, dom_bytes, dom_us, achieved = "propagate_group_kernel (walk steps >= 1; step 0 runs propagate_kernel)", prop_bytes_launch, 1e3 * prop_ms_per_launch, prop_achieved
+    dom_name, dom_bytes, dom_us, achieved = "propagate_group_kernel (walk steps >= 1; step 0 runs propagate_kernel)", prop_bytes_launch, 1e3 * prop_ms_per_launch, prop_achieved
     h2d = M.indptr.size * 8 + M.indices.size * 4 + M.data.size * 8 + n * 4
     traffic, traffic_src = measured_traffic(args.workload, args.dtype) if world == 1 else (None, None)
 
     line = {
         "metric": "crwr_walk_steps_per_s", "value": value,
-        "unit": "walk-steps/s" if world == 1 else "walk-steps/s x (markers/8000) [weak scaling aggregate]",
+        "unit": "walk-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": walk_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": config_dict(wl, world, args.dtype),
         "walk_steps_per_imputation": steps_per_walk, "us_per_walk_step": 1e3 * step_ms,
         "imputation_wall_ms_e2e": e2e_ms / args.steps,
@@ -358,7 +386,7 @@ def main():
                      "bytes_per_launch": dom_bytes, "us_per_launch": dom_us, "launches_per_imputation": kern_launches,
                      "propagate_kernel_alone": {"bytes_per_launch": prop_bytes_launch, "us_per_launch": 1e3 * prop_ms_per_launch,
                                                 "achieved": prop_achieved, "frac": prop_achieved / peak,
-                                                "note": "measured with one launch per phase (crwr_set_mode 0)"},
+                                                "note": "CUDA events around every launch, one profiled walk"},
                      "whole_step": {"bytes": total_bytes / max(steps_per_walk, 1), "us": 1e3 * step_ms,
                                     "achieved": step_gbs, "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0}},
         "e2e": {"value": e2e_value, "unit": "walk-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -367,6 +395,7 @@ def main():
                            "gather+finish": 1e3 * phases[2] / max(steps_per_walk - 1, 1),
                            "note": "CUDA-event durations inside one profiled walk (unsharded walks only)"},
         "gpu_launches": launches,
+        "result_sha256": result_sha256(E), "result_nnz": int(E.nnz),
         "clocks": sampler.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -374,12 +403,23 @@ def main():
         perm = oracle.marker_permutation(n, idx)
         P = oracle.transition_matrix(M, perm, np.float32)
         tr = oracle.WalkTrace()
-        t0 = time.perf_counter()
-        oracle.crwr_walk(P, 0.5, 80, 0.01, m, trace=tr)
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": len(tr.steps) / dt, "unit": "walk-steps/s", "cores": 1, "kind": "port",
-                                "sample": "one full float32 walk (%d steps, %.2f s) of the same workload; scipy.sparse and "
-                                          "np.percentile are serial: 1 of %d host cores used" % (len(tr.steps), dt, os.cpu_count())}
+        ref_walk, ref_root = _reference_walk()
+        if ref_walk is not None:
+            oracle.crwr_walk(P, 0.5, 80, 0.01, m, trace=tr)          # step count (untimed)
+            t0 = time.perf_counter()
+            ref_walk(P, 0.5, 80, 0.01, m)
+            dt = time.perf_counter() - t0
+        else:
+            t0 = time.perf_counter()
+            oracle.crwr_walk(P, 0.5, 80, 0.01, m, trace=tr)
+            dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": len(tr.steps) / dt, "unit": "walk-steps/s", "cores": 1,
+                                "kind": "reference" if ref_walk is not None else "port",
+                                "sample": "one full float32 walk (%d steps, %.2f s) of the same workload by %s; scipy.sparse and "
+                                          "np.percentile are serial: 1 of %d host cores used" % (
+                                              len(tr.steps), dt, "the unmodified Script.utility.random_walk_cpu" if ref_walk is not None
+                                              else "the oracle port (same scipy calls; the Python reference does not travel to the GPU box)",
+                                              os.cpu_count())}
     walker.close()
     if rank == 0:
         print(json.dumps(line))

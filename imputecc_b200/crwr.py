@@ -30,9 +30,6 @@ DEFAULT_TOL = 0.01          # imputation.py:120
 DEFAULT_MAX_STEPS = 500     # utility.py:281
 # walk steps enqueued between two status polls (steps after the stop rule fired are skipped on the device)
 POLL_EVERY = int(__import__("os").environ.get("CRWR_POLL_EVERY", "16"))
-PERSISTENT_POLL_EVERY = 16
-_m = __import__("os").environ.get("CRWR_WALK_MODE")
-WALK_MODE = int(_m) if _m is not None else None     # developer override of crwr_set_mode
 
 
 def _torch():
@@ -133,19 +130,18 @@ def default_iterate_cap(n_rows: int, n_contigs: int) -> int:
     return int(min(n_rows * n_contigs, max(1 << 22, 2048 * n_rows)))
 
 
-def poll_chunk(issued: int, persistent: bool = False) -> int:
+def poll_chunk(issued: int) -> int:
     """Walk steps to enqueue before the next status poll.
 
     Steps 0 and 1 change the row shapes most, so the kernel sizing hints are refreshed after each;
     after step 3 the kept share has been observed and the walk runs in long chunks.  Steps enqueued
-    after the stop rule fired are skipped on the device (three empty launches each, ~7 us, with one
-    launch per phase; free inside the persistent kernel) - cheaper than an extra poll (~28 us: stream
-    sync, status copy, relaunch gap) for walks of the usual 13-19 steps."""
+    after the stop rule fired are skipped on the device (a few empty launches each, ~7 us) - cheaper
+    than an extra poll (~28 us: stream sync, status copy, relaunch gap) for walks of the usual 13-19 steps."""
     if issued < 2:
         return 1
     if issued < 4:
         return 2
-    return PERSISTENT_POLL_EVERY if persistent else POLL_EVERY
+    return POLL_EVERY
 
 
 def next_row_hints(max_row_len: int, max_kept: int, perc: float, issued: int):
@@ -209,7 +205,6 @@ class Walker:
         self.regrows = 0
         self._walk_args = None
         self.hint_override = None      # tests pin the kernel sizing through this
-        self.mode = 0                  # crwr_set_mode: 0 = one launch per phase, 1 = persistent kernel
         self._create()
 
     # -- plumbing ---------------------------------------------------------------------------
@@ -326,15 +321,8 @@ class Walker:
             torch.cuda.current_stream(self.device).synchronize()
 
     # -- the walk -----------------------------------------------------------------------------
-    def set_mode(self, mode: int):
-        """0: one launch per phase (default); 1: persistent cooperative kernel per chunk of steps."""
-        _lib.check(self.lib.crwr_set_mode(self.handle, int(mode)))
-        self.mode = int(mode)
-
     def walk_init(self, rp, perc, tol=DEFAULT_TOL, max_steps=DEFAULT_MAX_STEPS):
         self._walk_args = (float(rp), float(perc), float(tol), int(max_steps))
-        if WALK_MODE is not None:
-            self.set_mode(WALK_MODE)
         _lib.check(self.lib.crwr_walk_init(self.handle, float(rp), float(perc), float(tol), int(max_steps), self._stream()))
 
     def poll(self) -> Status:
@@ -361,7 +349,7 @@ class Walker:
         hints = next_row_hints(0, 0, perc, 0)
         while True:
             # steps 0 and 1 change the row shapes most: poll after each; later run four at a time
-            chunk = poll_chunk(issued, self.mode == 1)
+            chunk = poll_chunk(issued)
             chunk = min(chunk, max_steps - issued)
             self.set_row_hints(*hints)
             _lib.check(lib.crwr_walk_enqueue(h, chunk, self._stream()))
@@ -528,25 +516,27 @@ def random_walk_b200(P, rp, perc, tol, num_marker_contig, *, max_steps: int = DE
 
 
 def crwr_impute(normcc, marker_idx_sorted, rp, perc, tol: float = DEFAULT_TOL, max_steps: int = DEFAULT_MAX_STEPS,
-                dtype=np.float32, device=None, return_info: bool = False, group=None):
+                dtype=np.float32, device=None, return_info: bool = False, group=None, iterate_cap: Optional[int] = None):
     """B-outer: NormCC matrix + sorted marker indices -> imputed m x m matrix.
 
     The statements of ``ImputeMatrix._imputation`` (imputation.py:112-127) on the GPU:
     transition matrix, walk, slice, symmetric normalisation.  Returns a scipy CSR matrix of the
     walk dtype (the caller applies ``.tolil()`` as imputation.py:129 does).  With a
-    ``torch.distributed`` process group the restart rows are sharded over its ranks.
+    ``torch.distributed`` process group the restart rows are sharded over its ranks.  ``iterate_cap``
+    overrides the initial capacity (entries) of the iterate buffers; they regrow when too small.
     """
     validate_inputs(normcc, marker_idx_sorted, rp, perc, check_values=False)
     if group is not None:
         from .sharded import crwr_impute_sharded
-        return crwr_impute_sharded(normcc, marker_idx_sorted, rp, perc, tol, max_steps, dtype, device, return_info, group)
+        return crwr_impute_sharded(normcc, marker_idx_sorted, rp, perc, tol, max_steps, dtype, device, return_info, group,
+                                   iterate_cap=iterate_cap)
     M = normcc if isinstance(normcc, sp.csr_matrix) else sp.csr_matrix(normcc)
     if not M.has_canonical_format:
         M = M.copy()
         M.sum_duplicates()
     idx = np.asarray(marker_idx_sorted, dtype=np.int64)
     n, m = M.shape[0], idx.size
-    w = Walker(n, m, dtype=dtype, device=device, transition_nnz_cap=int(M.nnz) + n)
+    w = Walker(n, m, dtype=dtype, device=device, transition_nnz_cap=int(M.nnz) + n, iterate_cap=iterate_cap)
     try:
         torch = _torch()
         with torch.cuda.device(w.device):

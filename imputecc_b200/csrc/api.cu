@@ -15,7 +15,6 @@
 #include "propagate_group.cuh"
 #include "transition.cuh"
 #include "finish.cuh"
-#include "walk.cuh"
 #include "peer.cuh"
 #include "binweights.cuh"
 
@@ -158,22 +157,14 @@ struct crwr_handle_s {
     bool have_p;
     bool walking;
     int steps_enqueued;
-    PropShape shape;                // run-time sizing of the warp-per-row propagate kernel (persistent mode)
-    int grid;                       // its persistent grid size
+    PropShape shape;                // run-time sizing of the warp-per-row propagate kernel (walk step 0)
+    int grid;                       // its grid size
     GroupShape gshape;              // run-time sizing of the row-group propagate kernel (default)
     int ggrid = 0;                  // its persistent grid size
     int prop_kind = 1;              // 1: row-group kernel (default), 0: warp-per-row kernel (CRWR_PROP=warp)
     bool order_valid = false;       // row_order holds the longest-first order of this walk (built before step kOrderStep)
     bool use_order = true;          // CRWR_ROW_ORDER=0: rows in index order
     int pdl_forced = -1;            // CRWR_PDL=0/1: programmatic dependent launch forced off/on (-1: by row length, use_pdl)
-    // 0 (default): one launch per phase.  1: one cooperative kernel per chunk of steps - measured equal for
-    // float32 small-row workloads and 10-15 % slower for float64 (small CTAs make CTA 0's serial scan/finish
-    // phases slower), so it is opt-in.
-    int mode = 0;
-    int mode_next = 0;              // takes effect at the next crwr_walk_init
-    bool coop_ok = false;           // device supports cooperative launches
-    int coop_grid = 0;              // co-resident CTAs of walk_chunk_kernel for the current shape
-    size_t coop_smem = 0;
     int max_smem_optin;
     double rp, perc;
     WalkState* h_state = nullptr;               // pinned host mirror of the device state (polls)
@@ -184,6 +175,7 @@ struct crwr_handle_s {
     unsigned long long* peer_block = nullptr;   // this rank's symmetric block
     unsigned long long peer_epoch_base = 0;
     bool hist0_fused = false;                   // sharded step: level-0 histogram already filled by propagate
+    bool bitmaps_zeroed = false;                // large-row kernel bitmaps cleared (first crwr_walk_init, caller's stream)
     bool profile = false;                       // CUDA events around every main propagate launch
     std::vector<cudaEvent_t> ev;                // start/end pairs
     std::vector<cudaEvent_t> marks;             // profile mode: step start + one event after each kernel of the step
@@ -256,24 +248,6 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
     if (per_sm < 1) per_sm = 1;
     h->shape = sh;
     h->grid = per_sm * h->sm_count;
-    // the persistent walk kernel shares the per-warp layout; its CTA also hosts the 4096-bin histogram of the
-    // level-1 pass and the finish step's scratch in the same dynamic shared memory
-    h->coop_grid = 0;
-    if (h->coop_ok) {
-        size_t cs = smem;
-        if (cs < (size_t)kSelectBins * sizeof(unsigned int)) cs = (size_t)kSelectBins * sizeof(unsigned int);
-        if (cs < kFinishScratchBytes) cs = kFinishScratchBytes;
-        cs = (cs + 255) & ~(size_t)255;
-        if (cs <= (size_t)h->max_smem_optin &&
-            cudaFuncSetAttribute(walk_chunk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs) == cudaSuccess) {
-            int cper = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cper, walk_chunk_kernel<T>, w * 32, cs) == cudaSuccess && cper >= 1) {
-                h->coop_grid = cper * h->sm_count;
-                h->coop_smem = cs;
-            }
-        }
-        (void)cudaGetLastError();
-    }
     return 0;
 }
 
@@ -585,46 +559,6 @@ DenseScratch<T> dense_scratch(crwr_handle_s* h) {
     return sc;
 }
 
-FinishArgs finish_args(crwr_handle_s* h, int do_select, const void* gathered);
-
-// One cooperative launch that runs up to n_steps walk steps (walk.cuh).
-template <typename T>
-int launch_walk_chunk(crwr_handle_s* h, int n_steps, cudaStream_t st) {
-    const Layout& L = h->L;
-    WalkChunkArgs<T> w;
-    w.prop = prop_args<T>(h, 0, true);
-    for (int b = 0; b < 2; ++b)
-        w.buf[b] = IterBuf<T>{h->at<int32_t>(L.it_cols[b]), h->at<T>(L.it_vals[b]), h->at<long long>(L.it_ptr[b]),
-                              h->at<int32_t>(L.it_len[b])};
-    w.shape = h->shape;
-    w.dense = dense_scratch<T>(h);
-    w.dense_warps = L.dense_warps;
-    w.fin = finish_args(h, 1, nullptr);
-    w.hist = hist_ptr(h);
-    w.cand_block = h->at<unsigned long long>(L.cand);
-    w.cand_cap = (unsigned long long)L.cand_cap;
-    w.n_steps = n_steps;
-    const int rows = w.prop.n_rows;
-    int grid = (rows + h->shape.warps - 1) / h->shape.warps;
-    if (grid > h->coop_grid) grid = h->coop_grid;
-    if (grid < 1) grid = 1;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (h->profile) {
-        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
-        cudaEventRecord(e0, st);
-    }
-    void* args[] = {(void*)&w};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)walk_chunk_kernel<T>, dim3(grid), dim3(h->shape.warps * 32), args,
-                                                h->coop_smem, st);
-    ++g_launches;
-    if (h->profile) {
-        cudaEventRecord(e1, st);
-        h->ev.push_back(e0);
-        h->ev.push_back(e1);
-    }
-    return e == cudaSuccess ? 0 : -1;
-}
-
 void prof_mark(crwr_handle_s* h, cudaStream_t st, int id) {
     if (!h->profile) return;
     cudaEvent_t e;
@@ -751,8 +685,9 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     h->cfg = *cfg;
     make_layout(*cfg, h->L);
     if ((int64_t)h->L.bytes > workspace_bytes) {
+        const long long need = (long long)h->L.bytes;
         delete h;
-        CRWR_FAIL(CRWR_ERR_INVALID, "workspace too small: need %lld bytes", (long long)h->L.bytes);
+        CRWR_FAIL(CRWR_ERR_INVALID, "workspace too small: need %lld bytes", need);
     }
     h->ws = (unsigned char*)d_workspace;
     int sm_count = 0, smem_optin = 0;
@@ -764,25 +699,18 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     h->walking = false;
     h->steps_enqueued = 0;
     h->max_smem_optin = smem_optin;
-    {
-        int coop = 0;
-        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device) == cudaSuccess) h->coop_ok = coop != 0;
-    }
     h->h_state = acquire_pinned_state();
     if (!h->h_state) {
         delete h;
         CRWR_FAIL(CRWR_ERR_CUDA, "cudaMallocHost failed");
     }
-    // the large-row kernel's bitmaps clean up after themselves: zero them once
-    if (cudaMemset(h->ws + h->L.d_tbits, 0, 4 * (size_t)h->L.words * h->L.dense_warps) != cudaSuccess ||
-        cudaMemset(h->ws + h->L.d_kbits, 0, 4 * (size_t)h->L.words * h->L.dense_warps) != cudaSuccess) {
-        release_pinned_state(h->h_state);
-        delete h;
-        CRWR_FAIL(CRWR_ERR_CUDA, "workspace memset failed");
-    }
+    h->bitmaps_zeroed = false;
+    // the large-row kernel's bitmaps clean up after themselves: they are zeroed once, on the caller's stream, by the
+    // first crwr_walk_init (bitmaps_zeroed)
     int e = cfg->dtype == CRWR_F64 ? configure_shape<double>(h, 192, 32) : configure_shape<float>(h, 192, 32);
     if (!e) e = cfg->dtype == CRWR_F64 ? configure_group_shape<double>(h, 192, 32) : configure_group_shape<float>(h, 192, 32);
     if (e) {
+        release_pinned_state(h->h_state);
         delete h;
         CRWR_FAIL(CRWR_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
     }
@@ -897,6 +825,11 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     cudaStream_t st = (cudaStream_t)stream;
     const Layout& L = h->L;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (!h->bitmaps_zeroed) {
+        CUDA_TRY(cudaMemsetAsync(h->ws + L.d_tbits, 0, 4 * (size_t)L.words * L.dense_warps, st));
+        CUDA_TRY(cudaMemsetAsync(h->ws + L.d_kbits, 0, 4 * (size_t)L.words * L.dense_warps, st));
+        h->bitmaps_zeroed = true;
+    }
     init_state_kernel<<<1, 256, 0, st>>>(h->at<WalkState>(L.state), rp, perc, tol, max_steps,
                                          h->at<unsigned long long>(L.xbuf), kXExtras + kSelectLevels * kSelectBins,
                                          h->at<unsigned long long>(L.cand));
@@ -917,7 +850,6 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     h->steps_enqueued = 0;
     h->order_valid = false;
     h->walking = true;
-    h->mode = h->mode_next;
     return CRWR_OK;
 }
 
@@ -1030,21 +962,6 @@ int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept)
     return CRWR_OK;
 }
 
-int32_t crwr_set_mode(crwr_handle h, int32_t mode) {
-    if (!h || (mode != 0 && mode != 1)) CRWR_FAIL(CRWR_ERR_INVALID, "mode must be 0 or 1");
-    h->mode_next = mode;            // applied by the next crwr_walk_init: a walk never changes mode midway
-    return CRWR_OK;
-}
-
-int32_t crwr_phase_ns(crwr_handle h, uint64_t* h_out8, void* stream) {
-    if (!h || !h_out8) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaMemcpyAsync(h->h_state, h->ws + h->L.state, sizeof(WalkState), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    for (int i = 0; i < 8; ++i) h_out8[i] = h->h_state->phase_ns[i];
-    return CRWR_OK;
-}
-
 int32_t crwr_get_shape(crwr_handle h, int64_t* h_out8) {
     if (!h || !h_out8) CRWR_FAIL(CRWR_ERR_INVALID, "null argument");
     h_out8[0] = h->shape.H; h_out8[1] = h->shape.limit; h_out8[2] = h->shape.kmax; h_out8[3] = h->shape.scap;
@@ -1066,14 +983,6 @@ int32_t crwr_walk_enqueue(crwr_handle h, int32_t n_steps, void* stream) {
         CRWR_FAIL(CRWR_ERR_STATE, "crwr_walk_enqueue is for unsharded walks; use the crwr_step_* calls");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    // the persistent kernel pays off when a step's phases are short (small rows: several warps per CTA); with
-    // one-warp CTAs (long rows) the separate launches are faster, and the choice can change between chunks
-    if (h->mode == 1 && h->coop_grid > 0 && h->shape.warps >= 2 && n_steps > 0) {
-        int e = h->cfg.dtype == CRWR_F64 ? launch_walk_chunk<double>(h, n_steps, st) : launch_walk_chunk<float>(h, n_steps, st);
-        if (e) CRWR_FAIL(CRWR_ERR_CUDA, "cooperative walk launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        h->steps_enqueued += n_steps;
-        return CRWR_OK;
-    }
     for (int i = 0; i < n_steps; ++i) {
         int e = h->cfg.dtype == CRWR_F64 ? enqueue_step<double>(h, st) : enqueue_step<float>(h, st);
         if (e) CRWR_FAIL(CRWR_ERR_CUDA, "step launch failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -44,9 +44,17 @@ __device__ __forceinline__ unsigned long long ld_peer(const unsigned long long* 
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // Cross-GPU barrier for one CTA per rank: publish `epoch` in every peer's flag slot for this rank, wait until
 // every peer's epoch has arrived here.  Epochs only grow, so flags never need resetting.  The wait is
-// bounded (a peer that died must not hang this GPU): on time-out the walk is flagged and stops.
+// bounded in wall time (a peer that died must not hang this GPU): 10 s inside a walk, two minutes at the first
+// barrier of a walk (nothing on the host aligns the ranks before it: a peer may still be uploading its matrix).
+// On time-out the walk is flagged, the caller skips its sums, and the finish step stops the walk.
 __device__ __forceinline__ void peer_barrier(const PeerInfo& p, unsigned long long epoch, WalkState* st) {
     __syncthreads();
     if (threadIdx.x == 0) __threadfence_system();
@@ -55,9 +63,10 @@ __device__ __forceinline__ void peer_barrier(const PeerInfo& p, unsigned long lo
         unsigned long long* remote = p.blocks[threadIdx.x] + p.rank;
         st_release_sys(remote, epoch);
         const unsigned long long* mine = p.blocks[p.rank] + threadIdx.x;
-        const long long t0 = clock64();
+        const unsigned long long limit = st->step == 0 ? 120000000000ull : 10000000000ull;
+        const unsigned long long t0 = global_ns();
         while (ld_acquire_sys(mine) < epoch) {
-            if (clock64() - t0 > 6000000000ll) { st->peer_timeout = 1; break; }     // ~3 s
+            if (global_ns() - t0 > limit) { st->peer_timeout = 1; break; }
         }
     }
     __syncthreads();
@@ -86,6 +95,7 @@ __global__ void __launch_bounds__(1024) peer_scan_kernel(WalkState* st, PeerInfo
         extras[kXFallback] = st->fb_count;
     }
     peer_barrier(p, epoch, st);
+    if (st->peer_timeout) return;                   // unsynchronised data is never consumed; finish stops the walk
     if (level <= 0 && t < kXExtras) {
         unsigned long long s = 0;
         for (int r = 0; r < p.world; ++r) s += ld_peer(p.blocks[r] + kPeerX + t);
@@ -133,7 +143,7 @@ __global__ void __launch_bounds__(1024) peer_finish_kernel(FinishArgs a, PeerInf
     unsigned long long* mine = p.blocks[p.rank];
     // always a barrier: on step 0 it protects the counters a slower peer may still be summing
     peer_barrier(p, epoch, a.st);
-    if (a.do_select) {
+    if (a.do_select && !a.st->peer_timeout) {
         const int cand_off = kPeerCand0 + parity * kPeerCandWords;
         for (int r = 0; r < p.world; ++r) {
             const unsigned long long* src = p.blocks[r] + cand_off;

@@ -21,6 +21,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import _lib
+from ._lib import CapacityError
 from .crwr import (DEFAULT_MAX_STEPS, DEFAULT_TOL, WalkInfo, Walker, markers_first_order, shard_rows, stack_row_blocks,
                    symmetrise_device, validate_inputs, _require_cuda, _torch)
 
@@ -137,12 +138,13 @@ class PeerExchange:
     Created once per (process group, device) and reused by successive walks; ``next_epoch_base`` hands every
     walk a fresh, strictly increasing range of barrier epochs so the flag words never need resetting."""
 
-    _cache = {}
+    _cache = []         # [(group object, device string, PeerExchange or None)]: keyed on the group itself, not id()
 
     def __init__(self, dist, group, device):
         torch = _torch()
         import torch.distributed._symmetric_memory as symm_mem
         lib = _lib.load()
+        self.dist, self.group = dist, group
         self.nbytes = int(lib.crwr_peer_block_bytes())
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -158,18 +160,56 @@ class PeerExchange:
 
     @classmethod
     def get(cls, dist, group, device):
-        key = (id(group), str(device))
-        if key not in cls._cache:
-            cls._cache[key] = cls(dist, group, device)
-        return cls._cache[key]
+        """The exchange of (group, device), or None when it cannot be set up on EVERY rank (the ranks agree through
+        an all-reduce, so either all of them use the peer path or all fall back to the collectives)."""
+        torch = _torch()
+        for g, d, ex in cls._cache:
+            if g is group and d == str(device):
+                return ex
+        ex, ok = None, 1
+        try:
+            if not _peer_topology_ok(dist, group, device):
+                ok = 0
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()):
+            try:
+                ex = cls(dist, group, device)
+            except Exception:
+                ex, ok = None, 0
+            flag = torch.tensor([1 if ex is not None else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if not int(flag.item()):
+                ex = None
+        cls._cache.append((group, str(device), ex))
+        return ex
 
     def next_epoch_base(self) -> int:
         self.walks += 1
         return self.walks << 32
 
     def attach(self, walker):
+        # no host barrier: the first device-side barrier of a walk waits up to two minutes for a late peer
         _lib.check(walker.lib.crwr_peer_attach(walker.handle, C.c_void_p(self.ptrs.data_ptr()), self.rank,
                                                C.c_uint64(self.next_epoch_base())))
+
+
+def _peer_topology_ok(dist, group, device) -> bool:
+    """All ranks of the group on this node, one GPU each, with peer access between every pair."""
+    torch = _torch()
+    world = dist.get_world_size(group)
+    if world > torch.cuda.device_count():
+        return False                      # more ranks than local GPUs: some live on another node
+    import socket
+    host = socket.gethostname()
+    names = [None] * world
+    dist.all_gather_object(names, (host, int(torch.device(device).index or 0)), group=group)
+    if len({h for h, _ in names}) != 1 or len({d for _, d in names}) != world:
+        return False
+    me = int(torch.device(device).index or 0)
+    return all(d == me or torch.cuda.can_device_access_peer(me, d) for _, d in names)
 
 
 def run_sharded_walk_peer(walker, perc, max_steps):
@@ -201,7 +241,8 @@ def run_sharded_walk_peer(walker, perc, max_steps):
 
 
 def peer_exchange_available(dist, group) -> bool:
-    """NVLink peer exchange needs NCCL ranks on one node and torch symmetric memory."""
+    """NVLink peer exchange needs NCCL ranks and torch symmetric memory (PeerExchange.get then checks that the ranks
+    share a node with peer access and falls back, on all ranks together, when the rendezvous fails)."""
     if os.environ.get("CRWR_SHARDED_EXCHANGE", "peer") != "peer":
         return False
     try:
@@ -245,7 +286,7 @@ def gather_row_blocks(dist, group, ip, ix, dt, rows_of_rank, m):
 
 
 def crwr_impute_sharded(normcc, marker_idx_sorted, rp, perc, tol=DEFAULT_TOL, max_steps=DEFAULT_MAX_STEPS,
-                        dtype=np.float32, device=None, return_info=False, group=None):
+                        dtype=np.float32, device=None, return_info=False, group=None, iterate_cap=None):
     """crwr_impute with the restart rows sharded over the ranks of ``group`` (default: WORLD).
 
     Every rank passes the same inputs and receives the same imputed matrix."""
@@ -268,18 +309,30 @@ def crwr_impute_sharded(normcc, marker_idx_sorted, rp, perc, tol=DEFAULT_TOL, ma
     new_of_old = markers_first_order(n, idx)
     ranges = shard_rows(m, world, weights=np.diff(M.indptr)[idx])
     r0, r1 = ranges[rank]
-    w = Walker(n, m, dtype=dtype, device=device, transition_nnz_cap=int(M.nnz) + n, row_range=(r0, r1), n_shards=world)
+    w = Walker(n, m, dtype=dtype, device=device, transition_nnz_cap=int(M.nnz) + n, row_range=(r0, r1), n_shards=world,
+               iterate_cap=iterate_cap)
     try:
         nnz_p = w.build_transition(M.indptr, M.indices, M.data, new_of_old)
         with torch.cuda.device(device):
-            use_peer = peer_exchange_available(dist, group)
-            if use_peer:
-                PeerExchange.get(dist, group, device).attach(w)
-            w.walk_init(rp, perc, tol, max_steps)
-            if use_peer:
-                st = run_sharded_walk_peer(w, perc, max_steps)
-            else:
-                st = run_sharded_walk(CudaPhases(w), TorchComm(dist, group), perc, max_steps)
+            peer = PeerExchange.get(dist, group, device) if peer_exchange_available(dist, group) else None
+            while True:
+                # capacity overflows are all-reduced inside the step, so every rank sees the error in the same poll
+                # and regrows in lockstep (the unsharded Walker.walk does the same)
+                try:
+                    if peer is not None:
+                        peer.attach(w)
+                    w.walk_init(rp, perc, tol, max_steps)
+                    if peer is not None:
+                        st = run_sharded_walk_peer(w, perc, max_steps)
+                    else:
+                        st = run_sharded_walk(CudaPhases(w), TorchComm(dist, group), perc, max_steps)
+                    break
+                except CapacityError as e:
+                    if "candidate" in str(e) and w.regrows >= 1:
+                        raise                 # more tied candidates than a shard block holds: a larger iterate buffer cannot help
+                    w.cap *= 2
+                    w.regrows += 1
+                    w._recreate()
             ip, ix, dt = w.result_device()
             f_ip, f_ix, f_dt = gather_row_blocks(dist, group, ip, ix, dt, ranges, m)
             e_ip, e_ix, e_dt = symmetrise_device(f_ip, f_ix, f_dt, m)

@@ -127,20 +127,11 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
  * crwr_status.max_row_len / max_kept. */
 int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept);
 int64_t crwr_transition_nnz(crwr_handle h);
-/* Persistent walk kernel diagnostics: nanoseconds CTA 0 spent, summed over the steps of the current walk, in
- * {propagate, barrier, scan, barrier, level-1 pass + gather, barrier, finish, barrier}.  Syncs the stream. */
-int32_t crwr_phase_ns(crwr_handle h, uint64_t* h_out8, void* stream);
 /* Current kernel sizing (diagnostics): {H, limit, kmax, scap, warps/CTA, smem bytes/warp, grid, SMs}. */
 int32_t crwr_get_shape(crwr_handle h, int64_t* h_out8);
 /* Sizing of the row-group propagate kernel (steps >= 1; diagnostics):
  * {table slots/row, max columns/row, max kept/row, overflow entries/row, lanes/row, warps/CTA, smem bytes/row, grid}. */
 int32_t crwr_get_group_shape(crwr_handle h, int64_t* h_out8);
-
-/* Execution mode of crwr_walk_enqueue: 0 (default) launches one kernel per phase of a step (always used by the
- * sharded walk); 1 runs a chunk of steps as ONE persistent cooperative kernel with grid barriers between the
- * phases (small-row shapes only; measured no faster on B200).  Results are identical.  Takes effect at
- * the next crwr_walk_init. */
-int32_t crwr_set_mode(crwr_handle h, int32_t mode);
 
 /* Enqueue up to n_steps walk steps (utility.py:282-304).  Stop rules are evaluated on the
  * device; steps enqueued after the walk has stopped are no-ops.  Single-shard walks only. */

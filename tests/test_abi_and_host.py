@@ -143,3 +143,17 @@ def test_synthetic_workloads_shape():
     assert (M != M.T).nnz == 0 and M.diagonal().sum() == 0 and M.has_sorted_indices
     assert idx.size == 320 and np.all(np.diff(idx) > 0)
     assert set(synth.WORKLOADS) >= {"c2_sparse", "c3_sparse", "c3_dense", "c4_sparse", "c4_dense"}
+
+
+def test_install_rebinding_without_gpu():
+    """install() only rebinds names; nothing runs until the reference calls them."""
+    import types
+    mod = types.ModuleType("stub")
+    mod.random_walk_cpu = lambda *a: None
+    mod.ImputeMatrix = type("ImputeMatrix", (), {"_imputation": lambda self: None})
+    pkg.install(mod, "inner")
+    assert mod.random_walk_cpu is pkg.random_walk_b200 and mod.ImputeMatrix._imputation is not pkg.imputation_b200
+    pkg.install(mod, "outer")
+    assert mod.ImputeMatrix._imputation is pkg.imputation_b200
+    with pytest.raises(ValueError):
+        pkg.install(mod, "both")
