@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CRWR_LIB", os.path.join(_HERE, "libcrwr_b200.so"))
 
 CRWR_F32, CRWR_F64 = 0, 1
-CRWR_OK, CRWR_ERR_INVALID, CRWR_ERR_CUDA, CRWR_ERR_CAPACITY, CRWR_ERR_STATE = 0, -1, -2, -3, -4
+CRWR_OK, CRWR_ERR_INVALID, CRWR_ERR_CUDA, CRWR_ERR_CAPACITY, CRWR_ERR_STATE, CRWR_ERR_RETRY = 0, -1, -2, -3, -4, -5
 STOP_NAMES = {0: "running", 1: "tolerance", 2: "plateau", 3: "max_steps"}
 
 
@@ -21,7 +21,7 @@ class Config(C.Structure):
 class StepRecord(C.Structure):
     _fields_ = [("nnz_in", C.c_int64), ("nnz_new", C.c_int64), ("cut", C.c_double), ("delta", C.c_double),
                 ("cut_applied", C.c_int32), ("plateau_hits", C.c_int32), ("fallback_rows", C.c_int32),
-                ("max_row_len", C.c_int32), ("max_kept", C.c_int32), ("reserved", C.c_int32)]
+                ("max_row_len", C.c_int32), ("max_kept", C.c_int32), ("fast_rows", C.c_int32)]
 
 
 class Status(C.Structure):
@@ -38,6 +38,10 @@ class CrwrError(RuntimeError):
 
 class CapacityError(CrwrError):
     pass
+
+
+class RetryError(CrwrError):
+    """The walk must be run again from crwr_walk_init; the handle has adapted itself."""
 
 
 _P = C.c_void_p
@@ -115,6 +119,8 @@ def check(code):
     msg = load().crwr_last_error().decode("utf-8", "replace")
     if code == CRWR_ERR_CAPACITY:
         raise CapacityError(code, msg)
+    if code == CRWR_ERR_RETRY:
+        raise RetryError(code, msg)
     if code == CRWR_ERR_INVALID:
         raise ValueError(msg)
     raise CrwrError(code, msg)

@@ -24,7 +24,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import _lib
-from ._lib import CRWR_F32, CRWR_F64, CapacityError, Config, Status, StepRecord
+from ._lib import CRWR_F32, CRWR_F64, CapacityError, Config, RetryError, Status, StepRecord
 
 DEFAULT_TOL = 0.01          # imputation.py:120
 DEFAULT_MAX_STEPS = 500     # utility.py:281
@@ -158,8 +158,9 @@ def next_row_hints(max_row_len: int, max_kept: int, perc: float, issued: int):
         # planted partitions) the step-0 row length.  A short hint sends rows to the slow large-row kernel.
         return 14 * max_row_len, max_row_len
     if issued < 3:
-        # first cut steps: rows may still grow a little; the kept share is not yet observed
-        return max_row_len + max_row_len // 2, int(max_row_len * min(1.0, 2.0 * (1.0 - perc / 100.0) + 0.05))
+        # first cut steps: rows may still grow a little, the kept share is not yet observed, and the first structure
+        # build consumes a superset of the kept entries (structure.cuh) that reaches more columns
+        return 2 * max_row_len, int(max_row_len * min(1.0, 2.5 * (1.0 - perc / 100.0) + 0.05))
     return max_row_len, max_kept
 
 
@@ -203,6 +204,7 @@ class Walker:
         self.handle = C.c_void_p()
         self.ws = None
         self.regrows = 0
+        self.retries = 0
         self._walk_args = None
         self.hint_override = None      # tests pin the kernel sizing through this
         self._create()
@@ -341,6 +343,8 @@ class Walker:
                     self.cap *= 2
                     self.regrows += 1
                     self._recreate()
+                except RetryError:
+                    self.retries += 1        # rows were deferred behind a step that queued no large-row kernel
 
     def _walk_once(self, rp, perc, tol, max_steps) -> Status:
         self.walk_init(rp, perc, tol, max_steps)
@@ -377,7 +381,8 @@ class Walker:
             r = buf[i]
             out.append(dict(step=i, nnz_in=int(r.nnz_in), nnz_new=int(r.nnz_new), cut=float(r.cut),
                             cut_applied=bool(r.cut_applied), delta=float(r.delta), plateau_hits=int(r.plateau_hits),
-                            fallback_rows=int(r.fallback_rows), max_row_len=int(r.max_row_len), max_kept=int(r.max_kept)))
+                            fallback_rows=int(r.fallback_rows), max_row_len=int(r.max_row_len), max_kept=int(r.max_kept),
+                            fast_rows=int(r.fast_rows)))
         for a, b in zip(out, out[1:]):
             a["nnz_kept"] = b["nnz_in"] if a["cut_applied"] else a["nnz_new"]
         return out

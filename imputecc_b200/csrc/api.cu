@@ -13,6 +13,7 @@
 #include "select.cuh"
 #include "propagate.cuh"
 #include "propagate_group.cuh"
+#include "tail.cuh"
 #include "transition.cuh"
 #include "finish.cuh"
 #include "peer.cuh"
@@ -48,6 +49,17 @@ namespace {
 
 constexpr int kDenseWarpsPerCta = 4;
 constexpr int kOrderStep = 4;       // first walk step that hands rows out longest first (row lengths have settled by then)
+constexpr int kBuildStep = 2;       // first walk step whose row-group pass records row structures (the first one behind a cut)
+constexpr int kFastStep = 3;        // first walk step that runs the cached-structure kernel
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+double env_double(const char* name, double dflt) {
+    const char* e = getenv(name);
+    return e ? atof(e) : dflt;
+}
 
 // Launch with programmatic stream serialization (see pdl_wait in common.cuh) when `pdl`, else the ordinary way.
 template <typename... KArgs, typename... Args>
@@ -72,6 +84,8 @@ struct Layout {
     size_t d_acc, d_oldv, d_ord, d_tbits, d_kbits;
     size_t k1_row_cnt, k1_col_cnt, k1_col_ptr, k1_col_fill, k1_csc_row, k1_csc_val, k1_scale, k1_iso, k1_row_val;
     size_t k1_bad;
+    size_t rs, slow_list, pool;
+    size_t pool_bytes;
     size_t bytes;
     long long cand_cap;
     long long dense_warps;
@@ -142,6 +156,18 @@ bool make_layout(const crwr_config& c, Layout& L) {
     L.k1_iso = bump(off, 4 * (size_t)n);
     L.k1_row_val = bump(off, 8 * (size_t)pcap);
     L.k1_bad = bump(off, 8);
+    // cached row structures (structure.cuh): headers, the fast kernel's hand-over list, the pool.  A settled row costs
+    // about (2 + s) bytes per product plus ~10 per output; rebuilt blocks are only reclaimed by a pool reset, so the
+    // pool is sized well above the working set of the largest walk the iterate buffers can hold.
+    L.rs = bump(off, sizeof(RowStruct) * (size_t)rows);
+    L.slow_list = bump(off, 4 * (size_t)rows);
+    {
+        long long pb = (long long)(c.dtype == CRWR_F64 ? 80 : 48) * cap;
+        if (pb < (64ll << 20)) pb = 64ll << 20;
+        if (const char* e = getenv("CRWR_POOL_BYTES")) { const long long v = atoll(e); if (v >= 4096) pb = v; }
+        L.pool_bytes = (size_t)pb;
+    }
+    L.pool = bump(off, L.pool_bytes);
     L.bytes = (off + 255) & ~(size_t)255;
     return true;
 }
@@ -175,6 +201,15 @@ struct crwr_handle_s {
     unsigned long long* peer_block = nullptr;   // this rank's symmetric block
     unsigned long long peer_epoch_base = 0;
     bool hist0_fused = false;                   // sharded step: level-0 histogram already filled by propagate
+    bool structs_on = true;                     // CRWR_STRUCT=0: no cached row structures (row-group kernel every step)
+    int win_step = 6;                           // first walk step whose cut comes from the window select (CRWR_WIN_STEP; 0: never)
+    float alpha = 0.3f;                         // K+ = entries above alpha x cut (CRWR_STRUCT_ALPHA)
+    float win_scale = 2.5f, win_min = 0.004f, win_max = 0.15f, win_rel_max = 0.10f;
+    bool dense_always = false;                  // a step deferred rows while no large-row kernel was queued: always queue it
+    bool fb_seen = false;                       // this walk has deferred rows before (polled)
+    int fast_km = 0, fast_rpw = 0;              // sizing of the fast kernel (operand slots per row, rows per warp)
+    size_t fast_smem = 0;
+    bool dense_launched = true;                 // the step being enqueued has a large-row kernel behind its propagation
     bool bitmaps_zeroed = false;                // large-row kernel bitmaps cleared (first crwr_walk_init, caller's stream)
     bool profile = false;                       // CUDA events around every main propagate launch
     std::vector<cudaEvent_t> ev;                // start/end pairs
@@ -253,9 +288,15 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
 
 template <typename T, int G>
 int group_kernel_attr(size_t smem, int threads, int* per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(propagate_group_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(propagate_group_kernel<T, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, propagate_group_kernel<T, G>, threads, smem);
+    e = cudaFuncSetAttribute(propagate_group_kernel<T, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int a = 0, b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, propagate_group_kernel<T, G, false>, threads, smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, propagate_group_kernel<T, G, true>, threads, smem);
+    *per_sm = a > b ? a : b;
     return (int)e;
 }
 
@@ -353,6 +394,21 @@ int configure_group_shape(crwr_handle_s* h, long long max_row_len, long long max
     if (per_sm < 1) per_sm = 1;
     h->gshape = sh;
     h->ggrid = per_sm * h->sm_count;
+    // the fast kernel holds K+ and q of its rows in shared memory: as many operand slots per row as the row-group kernel
+    // accepts (a structure it built always fits), rows per warp by what a CTA may take
+    {
+        const int km = sh.kmax;
+        int rpw = 4;
+        while (rpw > 1 && fast_smem_bytes<T>(km, rpw) > (size_t)64 * 1024) rpw >>= 1;
+        const size_t fs = fast_smem_bytes<T>(km, rpw);
+        if (fs <= (size_t)h->max_smem_optin &&
+            cudaFuncSetAttribute(propagate_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs) == cudaSuccess) {
+            h->fast_km = km; h->fast_rpw = rpw; h->fast_smem = fs;
+        } else {
+            (void)cudaGetLastError();
+            h->fast_km = 0;         // rows this long stay on the row-group kernel
+        }
+    }
     return 0;
 }
 
@@ -405,6 +461,16 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     a.fused_select = fused ? 1 : 0;
     a.prefill_l1 = fused ? 1 : 0;
     a.row_order = h->order_valid ? h->at<int32_t>(L.row_order) : nullptr;
+    a.row_list_count = nullptr;
+    a.rs = h->at<RowStruct>(L.rs);
+    a.pool = h->at<unsigned char>(L.pool);
+    a.pool_cap = (unsigned long long)L.pool_bytes;
+    a.slow_list = h->at<int32_t>(L.slow_list);
+    a.build = 0;
+    a.alpha = h->alpha;
+    a.win_mode = 0;
+    a.cand = nullptr;
+    a.cand_cap = (unsigned long long)L.cand_cap;
     // a warp reserves output space for a few rows at a time (zero-padded leftovers are skipped by the select)
     {
         long long ch = 3 * (long long)h->hint_len_eff;
@@ -421,40 +487,71 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     return a;
 }
 
+unsigned long long* cand_ptr(crwr_handle_s* h, int step);
+
+template <typename T, bool BUILD>
+void launch_group(const GroupShape& sh, bool pdl, int grid, size_t smem, cudaStream_t st, const PropArgs<T>& a) {
+    switch (sh.G) {
+        case 4: launch_k(pdl, propagate_group_kernel<T, 4, BUILD>, grid, sh.warps * 32, smem, st, a, sh); break;
+        case 8: launch_k(pdl, propagate_group_kernel<T, 8, BUILD>, grid, sh.warps * 32, smem, st, a, sh); break;
+        case 16: launch_k(pdl, propagate_group_kernel<T, 16, BUILD>, grid, sh.warps * 32, smem, st, a, sh); break;
+        default: launch_k(pdl, propagate_group_kernel<T, 32, BUILD>, grid, sh.warps * 32, smem, st, a, sh); break;
+    }
+}
+
+// The propagation of one walk step: [fast kernel: rows with a usable cached structure] -> row-group kernel (the rest;
+// records structures from kBuildStep on; warp-per-row kernel on step 0) -> [large-row kernel: deferred rows].
+// fused: the large-row kernel's last CTA scans the histograms (unsharded walk, histogram select).
+// win_step: the step's cut comes from the window select (tail.cuh): values are classified against the window.
 template <typename T>
-int launch_propagate(crwr_handle_s* h, int parity, bool fused, cudaStream_t st) {
+int launch_propagate(crwr_handle_s* h, int parity, bool fused, bool win_step, cudaStream_t st) {
     PropArgs<T> a = prop_args<T>(h, parity, fused);
     if (!fused && h->cfg.n_shards > 1 && h->hist0_fused) {
         a.hist = hist_ptr(h);                       // sharded: histogram only, no scan tail
         a.prefill_l1 = h->peer_attached ? 1 : 0;    // peer exchange: level 1 pre-filled for the predicted bin
     }
+    const int step = h->steps_enqueued;
+    if (win_step) {
+        a.hist = hist_ptr(h);                       // used when the previous step could not set a window
+        a.prefill_l1 = 1;
+        a.fused_select = 0;
+        a.win_mode = 1;
+        a.cand = cand_ptr(h, step);
+    }
     const int rows = a.n_rows;
     const bool pdl = use_pdl(h);
+    const bool structs = h->structs_on && h->prop_kind == 1;
+    const bool use_fast = structs && step >= kFastStep && h->fast_km > 0;
+    a.build = (structs && step >= kBuildStep) ? 1 : 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
         if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
         cudaEventRecord(e0, st);
     }
-    if (h->prop_kind == 1 && h->use_order && !h->order_valid && h->steps_enqueued >= kOrderStep && rows >= 64) {
+    if (use_fast) {
+        const int R = kFastWarps * h->fast_rpw;
+        launch_k(pdl, propagate_fast_kernel<T>, (rows + R - 1) / R, kFastWarps * 32, h->fast_smem, st, a, h->fast_km, h->fast_rpw);
+        ++g_launches;
+        if (cudaGetLastError() != cudaSuccess) return -1;
+        // the row-group kernel walks the rows the fast kernel handed over
+        a.row_order = h->at<int32_t>(h->L.slow_list);
+        a.row_list_count = &h->at<WalkState>(h->L.state)->slow_count;
+    } else if (h->prop_kind == 1 && h->use_order && !h->order_valid && step >= kOrderStep && rows >= 64) {
         // the walk has settled (the host sized the kernels from the third poll): rows by length, once
         row_order_kernel<<<1, 1024, 0, st>>>(h->at<int32_t>(h->L.it_len[parity]), rows, h->at<int32_t>(h->L.row_order));
         ++g_launches;
         h->order_valid = true;
         a.row_order = h->at<int32_t>(h->L.row_order);
     }
-    if (h->prop_kind == 1 && h->steps_enqueued >= 1) {      // step 0 keeps scipy's storage order (warp-per-row kernel)
+    if (h->prop_kind == 1 && step >= 1) {      // step 0 keeps scipy's storage order (warp-per-row kernel)
         const GroupShape& sh = h->gshape;
         const int rpc = sh.warps * (32 / sh.G);          // rows per CTA and pass
         int grid = (rows + rpc - 1) / rpc;
         if (grid > h->ggrid) grid = h->ggrid;
         if (grid < 1) grid = 1;
         const size_t smem = sh.per_row * (size_t)rpc + kHistWin * sizeof(unsigned int);
-        switch (sh.G) {
-            case 4: launch_k(pdl, propagate_group_kernel<T, 4>, grid, sh.warps * 32, smem, st, a, sh); break;
-            case 8: launch_k(pdl, propagate_group_kernel<T, 8>, grid, sh.warps * 32, smem, st, a, sh); break;
-            case 16: launch_k(pdl, propagate_group_kernel<T, 16>, grid, sh.warps * 32, smem, st, a, sh); break;
-            default: launch_k(pdl, propagate_group_kernel<T, 32>, grid, sh.warps * 32, smem, st, a, sh); break;
-        }
+        if (a.build) launch_group<T, true>(sh, pdl, grid, smem, st, a);
+        else launch_group<T, false>(sh, pdl, grid, smem, st, a);
     } else {
         const PropShape& sh = h->shape;
         int grid = (rows + sh.warps - 1) / sh.warps;
@@ -469,18 +566,26 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, cudaStream_t st) 
         h->ev.push_back(e1);
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
-    const Layout& L = h->L;
-    DenseScratch<T> sc;
-    sc.acc = h->at<T>(L.d_acc);
-    sc.oldv = h->at<T>(L.d_oldv);
-    sc.ord = h->at<int32_t>(L.d_ord);
-    sc.tbits = h->at<uint32_t>(L.d_tbits);
-    sc.kbits = h->at<uint32_t>(L.d_kbits);
-    sc.n = h->cfg.n_contigs;
-    sc.words = L.words;
-    launch_k(pdl, propagate_dense_kernel<T, kDenseWarpsPerCta>, (int)(L.dense_warps / kDenseWarpsPerCta), kDenseWarpsPerCta * 32, 0, st, a, sc);
-    ++g_launches;
-    if (cudaGetLastError() != cudaSuccess) return -1;
+    // the large-row kernel: always behind a histogram-select step (its last CTA scans the histograms); behind a
+    // window-select step only when this walk has deferred rows before (a deferral it then misses is caught by the finish
+    // step and the host retries with the kernel always queued)
+    h->dense_launched = !win_step || h->dense_always || h->fb_seen;
+    if (h->dense_launched) {
+        a.row_order = nullptr;
+        a.row_list_count = nullptr;
+        const Layout& L = h->L;
+        DenseScratch<T> sc;
+        sc.acc = h->at<T>(L.d_acc);
+        sc.oldv = h->at<T>(L.d_oldv);
+        sc.ord = h->at<int32_t>(L.d_ord);
+        sc.tbits = h->at<uint32_t>(L.d_tbits);
+        sc.kbits = h->at<uint32_t>(L.d_kbits);
+        sc.n = h->cfg.n_contigs;
+        sc.words = L.words;
+        launch_k(pdl, propagate_dense_kernel<T, kDenseWarpsPerCta>, (int)(L.dense_warps / kDenseWarpsPerCta), kDenseWarpsPerCta * 32, 0, st, a, sc);
+        ++g_launches;
+        if (cudaGetLastError() != cudaSuccess) return -1;
+    }
     return 0;
 }
 
@@ -525,6 +630,10 @@ FinishArgs finish_args(crwr_handle_s* h, int do_select, const void* gathered) {
     a.cand_cap = (unsigned long long)L.cand_cap;
     a.trace = h->at<crwr_step_record>(L.trace);
     a.do_select = do_select;
+    // the step after this one is a window-select step: derive its window from this step's cut
+    a.next_win = (h->win_step > 0 && h->cfg.n_shards == 1 && h->steps_enqueued + 1 >= h->win_step) ? 1 : 0;
+    a.dense_launched = h->dense_launched ? 1 : 0;
+    a.win_scale = h->win_scale; a.win_min = h->win_min; a.win_max = h->win_max; a.win_rel_max = h->win_rel_max;
     return a;
 }
 
@@ -541,6 +650,19 @@ int launch_gather(crwr_handle_s* h, int out_parity, int fused, cudaStream_t st) 
 template <typename T>
 int launch_finish(crwr_handle_s* h, int do_select, const void* gathered, cudaStream_t st) {
     launch_k(use_pdl(h), finish_step_kernel<T>, 1, 1024, 0, st, finish_args(h, do_select, gathered));
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <typename T>
+int launch_tail(crwr_handle_s* h, int out_parity, cudaStream_t st) {
+    const Layout& L = h->L;
+    TailArgs a;
+    a.fin = finish_args(h, 1, nullptr);
+    a.vals = h->at<T>(L.it_vals[out_parity]);
+    a.cand = cand_ptr(h, h->steps_enqueued);
+    a.cand_cap = (unsigned long long)L.cand_cap;
+    launch_k(use_pdl(h), tail_kernel<T>, 1, 1024, 0, st, a);
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -576,13 +698,21 @@ int enqueue_step(crwr_handle_s* h, cudaStream_t st) {
     const int parity = step & 1;
     if (step == 0) {
         // no percentile cut on step 0 (utility.py:286)
-        if (launch_propagate<T>(h, parity, false, st)) return -1;
+        if (launch_propagate<T>(h, parity, false, false, st)) return -1;
         if (launch_finish<T>(h, 0, nullptr, st)) return -1;
+    } else if (h->win_step > 0 && step >= h->win_step) {
+        // settled walk: propagation kernels (values classified against the select window) -> one single-CTA tail
+        prof_mark(h, st, 0);
+        if (launch_propagate<T>(h, parity, false, true, st)) return -1;
+        prof_mark(h, st, 1);
+        prof_mark(h, st, 2);
+        if (launch_tail<T>(h, parity ^ 1, st)) return -1;
+        prof_mark(h, st, 3);
     } else {
         // propagate (+ level-0/1 histograms in its epilogue) -> large-row kernel (+ scans in its last CTA)
         // -> level-1 histogram pass (skipped on the device when the prediction held) -> gather (+ finish)
         prof_mark(h, st, 0);
-        if (launch_propagate<T>(h, parity, true, st)) return -1;
+        if (launch_propagate<T>(h, parity, true, false, st)) return -1;
         prof_mark(h, st, 1);
         if (launch_hist<T>(h, parity ^ 1, 1, 1, st)) return -1;
         prof_mark(h, st, 2);
@@ -717,6 +847,16 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     if (const char* k = getenv("CRWR_PROP")) h->prop_kind = strcmp(k, "warp") == 0 ? 0 : 1;
     if (const char* k = getenv("CRWR_PDL")) h->pdl_forced = atoi(k) != 0 ? 1 : 0;
     if (const char* k = getenv("CRWR_ROW_ORDER")) h->use_order = atoi(k) != 0;
+    h->structs_on = env_int("CRWR_STRUCT", 1) != 0;
+    h->win_step = env_int("CRWR_WIN_STEP", 6);
+    if (h->win_step > 0 && h->win_step < 2) h->win_step = 2;
+    if (h->prop_kind != 1) h->win_step = 0;         // the warp-per-row kernel only knows the histogram select
+    h->alpha = (float)env_double("CRWR_STRUCT_ALPHA", 0.3);
+    if (!(h->alpha > 0.f && h->alpha <= 1.f)) h->alpha = 0.3f;
+    h->win_scale = (float)env_double("CRWR_WIN_SCALE", 2.5);
+    h->win_min = (float)env_double("CRWR_WIN_MIN", 0.004);
+    h->win_max = (float)env_double("CRWR_WIN_MAX", 0.15);
+    h->win_rel_max = (float)env_double("CRWR_WIN_REL_MAX", 0.10);
     *out = h;
     return CRWR_OK;
 }
@@ -845,9 +985,12 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
         init_iterate_kernel<float><<<(rows + 255) / 256, 256, 0, st>>>(b, rows, (int)h->cfg.row_begin);
     }
     LAUNCH_CHECK();
+    CUDA_TRY(cudaMemsetAsync(h->ws + L.rs, 0, sizeof(RowStruct) * (size_t)rows, st));     // generation 0: no structure
     h->rp = rp;
     h->perc = perc;
     h->steps_enqueued = 0;
+    h->fb_seen = false;
+    h->dense_launched = true;
     h->order_valid = false;
     h->walking = true;
     return CRWR_OK;
@@ -1003,7 +1146,7 @@ int32_t crwr_step_propagate(crwr_handle h, void* stream) {
     STEP_PROLOGUE();
     // steps >= 1: the level-0 histogram is filled by the propagate epilogue (crwr_step_hist(0) then has nothing to do)
     h->hist0_fused = h->steps_enqueued >= 1;
-    int e = f64 ? launch_propagate<double>(h, parity, false, st) : launch_propagate<float>(h, parity, false, st);
+    int e = f64 ? launch_propagate<double>(h, parity, false, false, st) : launch_propagate<float>(h, parity, false, false, st);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "propagate launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (!h->peer_attached) {        // with the peer exchange the counters are published by crwr_step_peer_scan
         pack_exchange_kernel<<<1, 32, 0, st>>>(h->at<WalkState>(h->L.state), xbuf_ptr(h));
@@ -1125,6 +1268,11 @@ int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
     if (s.done && s.stop_reason == CRWR_STOP_RUNNING) out->stop_reason = CRWR_STOP_MAX_STEPS;
     // the host-side step counter follows the device: steps enqueued past the stop were skipped
     if (s.done) h->steps_enqueued = s.step;
+    if (s.last_fallback_rows > 0) h->fb_seen = true;
+    if (s.fb_unhandled) {
+        h->dense_always = true;
+        CRWR_FAIL(CRWR_ERR_RETRY, "rows were deferred in a step without a large-row kernel: walk again (the kernel is now always queued)");
+    }
     if (s.debug_error) CRWR_FAIL(CRWR_ERR_STATE, "internal bounds check %d failed (CRWR_DEBUG_CHECKS build)", s.debug_error);
     if (s.peer_timeout) CRWR_FAIL(CRWR_ERR_STATE, "a cross-GPU barrier timed out: a peer rank did not arrive");
     if (s.capacity_overflow) CRWR_FAIL(CRWR_ERR_CAPACITY, "iterate buffer overflow (capacity %lld entries)", (long long)h->cfg.iterate_cap);

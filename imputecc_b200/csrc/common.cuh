@@ -115,9 +115,22 @@ struct WalkState {
     int32_t pad5;
     int32_t debug_error;               // CRWR_DEBUG_CHECKS builds: highest failed bounds-check code (0 = none)
     int32_t order_hazard;              // sticky: unordered rows would have been consumed without a cut (never for positive data)
-    unsigned long long phase_ns[8];    // persistent kernel: summed nanoseconds per phase (CTA 0's view), diagnostics
     int32_t scan_done;                 // the level scans of this step already ran (in the propagate kernel's last CTA)
     int32_t unordered_rows;            // the row-group kernel wrote this step's rows in slot-claim order (valid only behind a cut)
+    // cached row structures (structure.cuh): rows whose kept set lies inside the cached superset take the fast kernel
+    unsigned long long pool_cursor;    // bytes of the structure pool in use
+    unsigned int pool_gen;             // structures of an older generation are invalid (pool reset)
+    int32_t pool_reset_req;            // a build did not fit: the finish step resets the pool
+    unsigned int slow_count;           // rows the fast kernel handed to the row-group kernel this step
+    unsigned int fast_rows;            // rows the fast kernel computed this step
+    unsigned int built_rows;           // structures built this step
+    int32_t fb_unhandled;              // sticky: rows were deferred in a step that launched no large-row kernel (host retries)
+    // window select (tail.cuh): the epilogues collect the values in [win_lo, win_hi) as percentile candidates
+    int32_t win_on;                    // the current step's epilogues classify against the window
+    unsigned long long win_lo, win_hi; // window bounds as order-preserving keys
+    unsigned long long win_below;      // values strictly below win_lo (this rank)
+    unsigned int win_miss_steps;       // diagnostics: steps whose window missed (full select in the tail kernel)
+    int32_t pad6;
 };
 
 // Exchange block 0 of a sharded walk: level-0 histogram followed by these extras (all uint64, SUM).
@@ -175,6 +188,15 @@ __device__ __forceinline__ Sq128 sq_diff(const Sq128& pos, const Sq128& neg) {
     return r;
 }
 
+
+// Cached symbolic structure of one restart row (structure.cuh).
+struct RowStruct {
+    long long off;          // byte offset of the row's block in the structure pool
+    int32_t nkp;            // |K+|: operand columns the structure covers
+    int32_t no;             // output columns
+    int32_t nprod;          // contributions (products)
+    uint32_t gen;           // pool generation the block belongs to; 0 = no structure
+};
 
 template <typename T>
 struct IterBuf {

@@ -40,7 +40,18 @@ struct PropArgs {
     int32_t chunk;              // entries a warp reserves from the product buffer at a time
     int32_t row_chunk;          // rows a warp takes from the row counter at a time
     int32_t prefill_l1;         // 1: also count level 1 for the level-0 bin predicted from the previous cut
-    const int32_t* row_order;   // row-group kernel: rows in the order they are handed out (longest first), or null
+    const int32_t* row_order;   // row-group kernel: rows in the order they are handed out (longest first / slow list), or null
+    // cached row structures and window select (structure.cuh, tail.cuh)
+    const unsigned int* row_list_count;   // device count of the rows listed in row_order (slow list), or null: n_rows
+    RowStruct* rs;              // [n_rows] structure headers
+    unsigned char* pool;        // structure pool
+    unsigned long long pool_cap;
+    int32_t* slow_list;         // fast kernel: rows it could not take
+    int32_t build;              // row-group kernel: consume the superset K+ and record the row's structure
+    float alpha;                // K+ = entries above alpha x cut
+    int32_t win_mode;           // classify values against the select window when the walk state has one
+    unsigned long long* cand;   // candidate block [count, successor, keys...] of the window select
+    unsigned long long cand_cap;
 };
 
 // Fused select, unsharded walk: once every value of the step is in the level-0 histogram, one CTA locates
@@ -205,6 +216,67 @@ __device__ __forceinline__ void hist_window_flush(unsigned long long* hist, cons
     for (int i = threadIdx.x; i < kHistWin; i += blockDim.x) {
         const unsigned c = win[i];
         if (c) atomicAdd(&hist[HistWindow<T>::base + i], (unsigned long long)c);
+    }
+}
+
+constexpr int kWinStage = 256;             // window candidates staged per CTA (shares the histogram window's shared memory)
+
+// ---------------------------------------------------------------------------------------------
+// Window select, producer side (consumer: tail.cuh).  Once the cut has settled the next cut is known to lie in
+// a narrow window [lo, hi) around the previous one; the epilogues then only count the values below the window,
+// collect the few inside it as candidates and track the smallest value at or above it - the whole-array
+// histogram and gather passes of the radix select disappear.  Candidates are staged per CTA in shared memory
+// and appended to the candidate block [count, successor, keys...] with one atomic per CTA.
+// ---------------------------------------------------------------------------------------------
+struct WinAcc {
+    unsigned long long below;       // values below the window seen by this thread
+    unsigned long long succ;        // smallest key >= hi seen by this thread
+};
+struct WinStage {
+    unsigned long long* keys;       // [kWinStage] shared memory
+    unsigned int* count;            // shared
+};
+template <typename T>
+__device__ __forceinline__ void win_classify(bool valid, T v, unsigned long long lo, unsigned long long hi, WinAcc& w,
+                                             const WinStage& s, unsigned long long* cand, unsigned long long cand_cap) {
+    if (!valid) return;
+    const unsigned long long key = (unsigned long long)KeyOf<T>::enc(v);
+    if (key < lo) { w.below += 1; return; }
+    if (key >= hi) { w.succ = key < w.succ ? key : w.succ; return; }
+    const unsigned int pos = atomicAdd(s.count, 1u);
+    if (pos < (unsigned)kWinStage) s.keys[pos] = key;
+    else {
+        const unsigned long long idx = atomicAdd(&cand[0], 1ull);
+        if (idx < cand_cap) cand[kCandHeader + idx] = key;
+    }
+}
+// CTA-wide, after a barrier that follows the last win_classify.
+__device__ __forceinline__ void win_flush(const WinAcc& w, const WinStage& s, unsigned long long* cand, unsigned long long cand_cap,
+                                          WalkState* st) {
+    __shared__ unsigned long long s_base, s_below, s_succ;
+    if (threadIdx.x == 0) { s_below = 0ull; s_succ = ~0ull; }
+    __syncthreads();
+    unsigned long long b = w.below, m = w.succ;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        b += __shfl_xor_sync(kFull, b, o);
+        const unsigned long long om = __shfl_xor_sync(kFull, m, o);
+        m = om < m ? om : m;
+    }
+    if (lane_id() == 0) {
+        if (b) atomicAdd(&s_below, b);
+        if (m != ~0ull) atomicMin(&s_succ, m);
+    }
+    const unsigned int n = *s.count < (unsigned)kWinStage ? *s.count : (unsigned)kWinStage;
+    if (threadIdx.x == 0 && n) s_base = atomicAdd(&cand[0], (unsigned long long)n);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_below) atomicAdd(&st->win_below, s_below);
+        if (s_succ != ~0ull) atomicMin(&cand[1], s_succ);
+    }
+    for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long o = s_base + i;
+        if (o < cand_cap) cand[kCandHeader + o] = s.keys[i];
     }
 }
 
@@ -678,7 +750,8 @@ __device__ __forceinline__ void dense_accumulate_row_of_p(const PropArgs<T>& a, 
 // Rows deferred by the main kernel, one per warp at a time; gw = this warp's slot in the dense scratch.
 // Ends with the warp's totals published; the caller flushes the histogram window after a CTA barrier.
 template <typename T>
-__device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScratch<T>& sc, long long gw, unsigned int* win) {
+__device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScratch<T>& sc, long long gw, unsigned int* win,
+                                           bool win_mode, WinAcc& wacc, const WinStage& stage) {
     const unsigned n_fb = __ldcg(&a.st->fb_count);
     const int lane = lane_id();
     T* acc = sc.acc + gw * sc.n;
@@ -690,6 +763,7 @@ __device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScra
     const T cut = (T)__ldcg(&a.st->cut);
     const bool pred_valid = a.prefill_l1 && __ldcg(&a.st->pred_valid) != 0;
     const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)__ldcg(&a.st->pred_prefix0);
+    const unsigned long long wlo = __ldcg(&a.st->win_lo), whi = __ldcg(&a.st->win_hi);
     WarpTotals wt;
     totals_init(wt);
 
@@ -768,12 +842,14 @@ __device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScra
                 one = v != (T)0;
             }
             nz += __popc(__ballot_sync(kFull, one));
-            if (a.hist) hist_values<T>(a.hist, win, one, v, pred_valid, pred0);
+            if (win_mode) win_classify<T>(one, v, wlo, whi, wacc, stage, a.cand, a.cand_cap);
+            else if (a.hist) hist_values<T>(a.hist, win, one, v, pred_valid, pred0);
         }
         if (diag_new) {
             if (lane == 0) sq_add(pos, (double)a.restart * (double)a.restart);
             if (a.restart != (T)0) nz += 1;
-            if (a.hist) hist_values<T>(a.hist, win, lane == 0 && a.restart != (T)0, a.restart, pred_valid, pred0);
+            if (win_mode) win_classify<T>(lane == 0 && a.restart != (T)0, a.restart, wlo, whi, wacc, stage, a.cand, a.cand_cap);
+            else if (a.hist) hist_values<T>(a.hist, win, lane == 0 && a.restart != (T)0, a.restart, pred_valid, pred0);
         }
         __syncwarp();
         // old entries: every kept column has its bit in kbits and its value in oldv
@@ -824,11 +900,17 @@ __global__ void __launch_bounds__(WARPS * 32) propagate_dense_kernel(PropArgs<T>
         if (a.fused_select && blockIdx.x == 0) scan_tail<T, WARPS * 32>(a.st, a.hist);
         return;
     }
+    __shared__ unsigned int s_wn;
     for (int i = threadIdx.x; i < kHistWin; i += WARPS * 32) win[i] = 0u;
+    if (threadIdx.x == 0) s_wn = 0u;
     __syncthreads();
-    dense_rows<T>(a, sc, (long long)blockIdx.x * WARPS + (threadIdx.x >> 5), win);
+    const bool win_mode = a.win_mode && a.st->win_on != 0;
+    const WinStage stage = {reinterpret_cast<unsigned long long*>(win), &s_wn};
+    WinAcc wacc = {0ull, ~0ull};
+    dense_rows<T>(a, sc, (long long)blockIdx.x * WARPS + (threadIdx.x >> 5), win, win_mode, wacc, stage);
     __syncthreads();
-    if (a.hist) hist_window_flush<T>(a.hist, win);
+    if (win_mode) win_flush(wacc, stage, a.cand, a.cand_cap, a.st);
+    else if (a.hist) hist_window_flush<T>(a.hist, win);
 
     // ---- fused select (unsharded walk) when rows were deferred: the histogram is complete only now
     if (a.fused_select && !a.st->scan_done && last_block(&a.st->tick_dense)) scan_tail<T, WARPS * 32>(a.st, a.hist);
@@ -842,6 +924,7 @@ __global__ void init_state_kernel(WalkState* st, double rp, double perc, double 
         WalkState s;
         memset(&s, 0, sizeof(s));
         s.rp = rp; s.perc = perc; s.tol = tol; s.max_steps = max_steps;
+        s.pool_gen = 1u;
         *st = s;
         cand_block[0] = 0ull;
         cand_block[1] = ~0ull;

@@ -123,13 +123,12 @@ __device__ __noinline__ void scan_level(WalkState* st, const unsigned long long*
     __syncthreads();
 }
 
-// Block-wide radix select of local rank r among cand[0..c) (keys share their top 24 bits), 8 bits at
-// a time.  Returns the key, the number of candidates strictly below it and its multiplicity.
-template <int KBITS>
-__device__ void block_radix_select(const unsigned long long* cand, unsigned long long c, unsigned long long r,
+// Block-wide radix select of local rank r among cand[0..c) (keys share all bits above their low `free_bits`),
+// 8 bits at a time.  Returns the key, the number of candidates strictly below it and its multiplicity.
+__device__ void block_radix_select(const unsigned long long* cand, unsigned long long c, unsigned long long r, int free_bits,
                                    unsigned int* sh_hist, unsigned long long* sh_io, unsigned long long& key_out,
                                    unsigned long long& below_out, unsigned long long& dup_out) {
-    int remaining = KBITS - 2 * kSelectBits;
+    int remaining = free_bits;
     unsigned long long known = 0, mask = 0, below = 0, cnt = c;
     while (remaining > 0) {
         const int d = remaining >= 8 ? 8 : remaining;
@@ -141,17 +140,28 @@ __device__ void block_radix_select(const unsigned long long* cand, unsigned long
             if ((key & mask) == known) atomicAdd(&sh_hist[(unsigned)(key >> shift) & ((1u << d) - 1u)], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long run = below;
-            unsigned int b = 0;
-            for (; b + 1 < (1u << d); ++b) {
-                unsigned long long nb = run + sh_hist[b];
-                if (r < nb) break;
-                run = nb;
+        if (threadIdx.x < 32) {
+            // warp scan of the (up to) 256 bins, 8 per lane
+            const int l = threadIdx.x;
+            unsigned int cs[8];
+            unsigned int mine = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { cs[i] = (l * 8 + i) < (1 << d) ? sh_hist[l * 8 + i] : 0u; mine += cs[i]; }
+            unsigned int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int v = __shfl_up_sync(kFull, incl, o);
+                if (l >= o) incl += v;
             }
-            sh_io[0] = run;
-            sh_io[1] = b;
-            sh_io[2] = sh_hist[b];
+            unsigned long long run = below + (unsigned long long)(incl - mine);
+            // the bin holding rank r lies in exactly one lane's range (r < below + c always holds)
+            if (r >= run && r < run + mine) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (r >= run && r < run + cs[i]) { sh_io[0] = run; sh_io[1] = (unsigned long long)(l * 8 + i); sh_io[2] = cs[i]; }
+                    run += cs[i];
+                }
+            }
         }
         __syncthreads();
         below = sh_io[0];
@@ -161,7 +171,7 @@ __device__ void block_radix_select(const unsigned long long* cand, unsigned long
         remaining = shift;
         __syncthreads();
     }
-    key_out = (cand[0] & ~mask) | known;   // the top 24 bits are common to all candidates
+    key_out = (cand[0] & ~mask) | known;   // the bits above the free ones are common to all candidates
     below_out = below;
     dup_out = cnt;
 }
@@ -178,14 +188,18 @@ struct FinishArgs {
     unsigned long long cand_cap;          // keys per block
     crwr_step_record* trace;
     int32_t do_select;                    // 0 on step 0 (utility.py:286)
+    int32_t next_win;                     // 1: derive a select window for the next step from this step's cut (tail.cuh)
+    int32_t dense_launched;               // 0: the step launched no large-row kernel, deferred rows are an error (host retries)
+    float win_scale, win_min, win_max, win_rel_max;   // window half-width = clamp(win_scale x |relative move of the cut|, win_min, win_max)
 };
 
 // Shared-memory scratch the finish step needs (carved from the caller's buffer, 16-byte aligned).
 constexpr size_t kFinishScratchBytes = sizeof(unsigned long long) * (kCandSmem + 4 + 32 + 4) + sizeof(unsigned int) * 256 +
                                        sizeof(int) * 4 + ((sizeof(WalkState) + 15) / 16) * 16 + 64;
 
+// free_bits: low key bits in which the candidates may differ (-1: everything below the 24-bit prefix of the gather pass)
 template <typename T>
-__device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned char* scratch) {
+__device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned char* scratch, int free_bits = -1) {
     typedef KeyOf<T> KO;
     typedef typename KO::type K;
     unsigned long long* sk = reinterpret_cast<unsigned long long*>(scratch);
@@ -245,7 +259,7 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
         }
         if (s_ovf) {
             // handled below (sticky error)
-        } else if (c <= (unsigned long long)kCandSmem) {
+        } else if (c <= (unsigned long long)(free_bits >= 0 ? 512 : kCandSmem)) {
             for (unsigned int i = t; i < c; i += blockDim.x) sk[i] = cand[i];
             __syncthreads();
             for (unsigned int i = t; i < c; i += blockDim.x) {
@@ -261,7 +275,7 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
             __syncthreads();
         } else {
             unsigned long long key, below, dup;
-            block_radix_select<KO::bits>(cand, c, r, sh_hist, sh_io, key, below, dup);
+            block_radix_select(cand, c, r, free_bits >= 0 ? free_bits : KO::bits - 2 * kSelectBits, sh_hist, sh_io, key, below, dup);
             if (r + 1 < below + dup) {
                 if (t == 0) { s_xk = key; s_xk1 = key; s_have1 = 1; }
             } else {
@@ -334,8 +348,29 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
             rec.fallback_rows = (int)fb;
             rec.max_row_len = st->max_row_len;
             rec.max_kept = st->max_kept;
-            rec.reserved = 0;
+            rec.fast_rows = (int)st->fast_rows;
             a.trace[step] = rec;
+        }
+        // deferred rows with no large-row kernel behind the propagation: the step is incomplete, the host retries
+        if (fb > 0 && !a.dense_launched) st->fb_unhandled = 1;
+        // a structure build did not fit the pool: start a new generation (every row rebuilds on its next slow pass)
+        if (st->pool_reset_req) { st->pool_cursor = 0; st->pool_gen += 1; st->pool_reset_req = 0; }
+        // select window of the next step: the cut moves less and less, so it will lie within a few times its last move
+        {
+            int on = 0;
+            if (a.next_win && cut_applied && st->cut_on && st->cut > 0.0) {
+                const double c0 = st->cut, c1 = cut;
+                const double rel = fabs(c1 - c0) / c1;
+                double dl = (double)a.win_scale * rel;
+                dl = dl < (double)a.win_min ? (double)a.win_min : (dl > (double)a.win_max ? (double)a.win_max : dl);
+                const T lo = (T)(c1 * (1.0 - dl)), hi = (T)(c1 * (1.0 + dl));
+                if (rel <= (double)a.win_rel_max && lo > (T)0 && hi > lo) {
+                    on = 1;
+                    st->win_lo = (unsigned long long)KO::enc(lo);
+                    st->win_hi = (unsigned long long)KO::enc(hi);
+                }
+            }
+            st->win_on = on;
         }
         // rows written in slot-claim order (row-group kernel) are only valid operands behind a cut
         if (st->unordered_rows && a.do_select && !cut_applied && st->n_total > 0 && !st->capacity_overflow && !st->select_overflow)
@@ -347,7 +382,7 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
         st->parity ^= 1;
         st->step = step + 1;
         if (!done && step + 1 >= st->max_steps) { done = 1; reason = CRWR_STOP_MAX_STEPS; }
-        if (st->capacity_overflow || st->select_overflow || st->peer_timeout || st->order_hazard) done = 1;
+        if (st->capacity_overflow || st->select_overflow || st->peer_timeout || st->order_hazard || st->fb_unhandled) done = 1;
         st->done = done;
         st->stop_reason = reason;
         st->last_fallback_rows = (int)fb;
@@ -370,6 +405,7 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
         st->tick_dense = 0; st->tick_hist1 = 0; st->tick_gather = 0; st->tick_prop = 0;
         st->scan_done = 0;
         st->hist1_ready = 0;
+        st->slow_count = 0; st->fast_rows = 0; st->built_rows = 0; st->win_below = 0;
         if (cut_applied) {      // the next cut most likely falls into the same level-0 bin
             st->pred_prefix0 = (unsigned long long)(KO::enc((T)cut) >> (KO::bits - kSelectBits));
             st->pred_valid = 1;

