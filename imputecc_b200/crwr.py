@@ -340,6 +340,8 @@ class Walker:
                 try:
                     return self._walk_once(rp, perc, tol, max_steps)
                 except CapacityError:
+                    if self.cap > 256 * default_iterate_cap(self.rows, self.n):    # not a sizing problem any more
+                        raise
                     self.cap *= 2
                     self.regrows += 1
                     self._recreate()

@@ -8,6 +8,7 @@
 #include <mutex>
 #include <cmath>
 #include <utility>
+#include <map>
 
 #include "common.cuh"
 #include "select.cuh"
@@ -49,8 +50,6 @@ namespace {
 
 constexpr int kDenseWarpsPerCta = 4;
 constexpr int kOrderStep = 4;       // first walk step that hands rows out longest first (row lengths have settled by then)
-constexpr int kBuildStep = 2;       // first walk step whose row-group pass records row structures (the first one behind a cut)
-constexpr int kFastStep = 3;        // first walk step that runs the cached-structure kernel
 
 int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
@@ -77,6 +76,20 @@ cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, 
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// The dynamic shared-memory limit is an attribute of the kernel, not of a handle: walkers with different shapes share
+// it, so it only ever grows (every launch states its own size).
+std::map<const void*, size_t> g_smem_attr;
+std::mutex g_smem_attr_mutex;
+template <typename K>
+cudaError_t raise_smem_attr(K kernel, size_t smem) {
+    std::lock_guard<std::mutex> lock(g_smem_attr_mutex);
+    size_t& cur = g_smem_attr[(const void*)kernel];
+    if (smem <= cur) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) cur = smem;
+    return e;
+}
+
 struct Layout {
     size_t state, trace, p_indptr, p_cols, p_vals;
     size_t it_cols[2], it_vals[2], it_ptr[2], it_len[2];
@@ -84,8 +97,10 @@ struct Layout {
     size_t d_acc, d_oldv, d_ord, d_tbits, d_kbits;
     size_t k1_row_cnt, k1_col_cnt, k1_col_ptr, k1_col_fill, k1_csc_row, k1_csc_val, k1_scale, k1_iso, k1_row_val;
     size_t k1_bad;
-    size_t rs, slow_list, pool;
+    size_t rs, slow_list, pool, sym_tmp;
     size_t pool_bytes;
+    long long fixed_base, slot_cap; // first entry / entries of the fixed-slot region behind the per-step entries of both iterate buffers
+    int sym_tmp_cap;                // products per staging region of the symbolic kernel
     size_t bytes;
     long long cand_cap;
     long long dense_warps;
@@ -112,9 +127,13 @@ bool make_layout(const crwr_config& c, Layout& L) {
     L.p_indptr = bump(off, 4 * (size_t)(n + 1));
     L.p_cols = bump(off, 4 * (size_t)pcap);
     L.p_vals = bump(off, s * (size_t)pcap);
+    // iterate buffers: [cap per-step entries | slot_cap fixed-slot entries (rows with a cached structure, structure.cuh)]
+    // The fixed region starts on a 16-entry boundary (bulk copies) and has as many entries as the per-step region.
+    L.fixed_base = (cap + 15) & ~15ll;
+    L.slot_cap = L.fixed_base;
     for (int b = 0; b < 2; ++b) {
-        L.it_cols[b] = bump(off, 4 * (size_t)cap);
-        L.it_vals[b] = bump(off, s * (size_t)cap);
+        L.it_cols[b] = bump(off, 4 * (size_t)(L.fixed_base + L.slot_cap));
+        L.it_vals[b] = bump(off, s * (size_t)(L.fixed_base + L.slot_cap));
         L.it_ptr[b] = bump(off, 8 * (size_t)rows);
         L.it_len[b] = bump(off, 4 * (size_t)rows);
     }
@@ -156,9 +175,10 @@ bool make_layout(const crwr_config& c, Layout& L) {
     L.k1_iso = bump(off, 4 * (size_t)n);
     L.k1_row_val = bump(off, 8 * (size_t)pcap);
     L.k1_bad = bump(off, 8);
-    // cached row structures (structure.cuh): headers, the fast kernel's hand-over list, the pool.  A settled row costs
-    // about (2 + s) bytes per product plus ~10 per output; rebuilt blocks are only reclaimed by a pool reset, so the
-    // pool is sized well above the working set of the largest walk the iterate buffers can hold.
+    // cached row structures (structure.cuh): headers, the fast kernel's hand-over list, the pool, the symbolic kernel's
+    // staging regions.  A row costs about (2 + s) bytes per product plus ~10 per output; rebuilt blocks are never
+    // reclaimed during a walk, so the pool is sized well above the working set of the largest walk the iterate buffers
+    // can hold (running out is a capacity error: the host regrows the workspace).
     L.rs = bump(off, sizeof(RowStruct) * (size_t)rows);
     L.slow_list = bump(off, 4 * (size_t)rows);
     {
@@ -168,6 +188,15 @@ bool make_layout(const crwr_config& c, Layout& L) {
         L.pool_bytes = (size_t)pb;
     }
     L.pool = bump(off, L.pool_bytes);
+    {
+        long long tc = pcap < 16384 ? pcap : 16384;         // a row's products are at most nnz(P)
+        if (tc < 1024) tc = 1024;
+        tc = (tc + 7) & ~7ll;
+        L.sym_tmp_cap = (int)tc;
+        const long long ctas = rows < kSymMaxCtas ? rows : kSymMaxCtas;
+        L.sym_tmp = bump(off, (size_t)ctas * sym_tmp_bytes((int)tc, s));
+    }
+
     L.bytes = (off + 255) & ~(size_t)255;
     return true;
 }
@@ -207,8 +236,13 @@ struct crwr_handle_s {
     float win_scale = 2.5f, win_min = 0.004f, win_max = 0.15f, win_rel_max = 0.10f;
     bool dense_always = false;                  // a step deferred rows while no large-row kernel was queued: always queue it
     bool fb_seen = false;                       // this walk has deferred rows before (polled)
-    int fast_km = 0, fast_rpw = 0;              // sizing of the fast kernel (operand slots per row, rows per warp)
-    size_t fast_smem = 0;
+    SymShape sym = {0, 0, 0, 0, 0, 0, 0, 0};    // sizing of the symbolic kernel (structure.cuh)
+    int sym_grid = 0;
+    int fast_no = 0, fast_grid = 0;             // fast kernel: outputs per row it holds (0: kernel unusable), persistent grid
+    FastShape fshape = {0, 0, 0, 0};
+    long long avg_hot = 0;                      // mean pool bytes per row of this walk's structures (polled; 0: unknown)
+    bool fast_retune = false;                   // avg_hot moved: the next crwr_set_row_hints sizes the fast kernel again
+    int build_step = 2;                         // first walk step that runs the symbolic kernel (CRWR_BUILD_STEP, >= 2)
     bool dense_launched = true;                 // the step being enqueued has a large-row kernel behind its propagation
     bool bitmaps_zeroed = false;                // large-row kernel bitmaps cleared (first crwr_walk_init, caller's stream)
     bool profile = false;                       // CUDA events around every main propagate launch
@@ -216,6 +250,8 @@ struct crwr_handle_s {
     std::vector<cudaEvent_t> marks;             // profile mode: step start + one event after each kernel of the step
     std::vector<int> mark_ids;
     double phase_ms[4] = {0, 0, 0, 0};
+    bool timeline = false;                      // CRWR_TIMELINE=1 (developer aid): an event after every kernel of a profiled walk,
+    std::vector<std::pair<cudaEvent_t, const char*>> tl;   // durations printed to stderr by crwr_profile_read
     template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
 };
 
@@ -275,7 +311,7 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
     while (w & (w - 1)) --w;        // power of two: block-wide scans are templated on the CTA size
     sh.warps = w;
     const size_t smem = sh.per_warp * (size_t)w + kHistWin * sizeof(unsigned int);
-    cudaError_t e = cudaFuncSetAttribute(propagate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_smem_attr(propagate_kernel<T>, smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagate_kernel<T>, w * 32, smem);
@@ -287,17 +323,90 @@ int configure_shape(crwr_handle_s* h, long long max_row_len, long long max_kept)
 }
 
 template <typename T, int G>
-int group_kernel_attr(size_t smem, int threads, int* per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(propagate_group_kernel<T, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+int group_kernel_attr(size_t smem, int threads, int* per_sm, int) {
+    cudaError_t e = raise_smem_attr(propagate_group_kernel<T, G>, smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(propagate_group_kernel<T, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    int a = 0, b = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, propagate_group_kernel<T, G, false>, threads, smem);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, propagate_group_kernel<T, G, true>, threads, smem);
-    *per_sm = a > b ? a : b;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, propagate_group_kernel<T, G>, threads, smem);
     return (int)e;
+}
+
+// Sizes the symbolic and the fast kernel (structure.cuh) from the caller's hints: outputs and operand columns per row.
+template <typename T>
+int configure_struct_shape(crwr_handle_s* h, long long max_row_len, long long max_kept) {
+    const long long n = h->cfg.n_contigs;
+    const long long rows = h->cfg.row_end - h->cfg.row_begin;
+    const size_t win_bytes = kHistWin * sizeof(unsigned int);
+    long long no = round_up(max_row_len + max_row_len * 3 / 10 + 32, 32);
+    if (no < 128) no = 128;
+    if (no > n + 1) no = round_up(n + 1, 32);
+    long long km = round_up(max_kept + max_kept * 3 / 10 + 16, 32);
+    if (km < 64) km = 64;
+    if (km > no) km = no;
+    SymShape sh;
+    // shared-memory staging for rows of up to ~16 products per output (longer rows stage in global memory)
+    const double avg_deg = h->p_nnz > 0 ? (double)h->p_nnz / (double)n : 8.0;
+    for (;;) {
+        if (no > 65504) no = 65504;
+        if (km > no) km = no;
+        long long H = 512;
+        while (H < 2 * no + 64) H <<= 1;
+        long long ts = round_up((long long)((double)km * avg_deg * 1.25) + 256, 64);
+        if (ts > 8192) ts = 8192;
+        if (ts > h->L.sym_tmp_cap) ts = h->L.sym_tmp_cap;
+        sh.H = (int)H; sh.no_max = (int)no; sh.km = (int)km; sh.tmp_smem = (int)ts;
+        sh.smem = sym_smem_bytes(sh.H, sh.no_max, sh.km, sh.tmp_smem, sizeof(T));
+        if (sh.smem + 1024 <= (size_t)h->max_smem_optin) break;
+        no = round_up(no * 3 / 4, 32);          // too big for one SM: larger rows go to the large-row kernel
+    }
+    sh.tmp_cap = h->L.sym_tmp_cap;
+    sh.threads = env_int("CRWR_SYM_THREADS", 256);
+    sh.threads_build = env_int("CRWR_SYM_THREADS_BUILD", 128);
+    if (sh.threads < 32 || sh.threads > 256 || (sh.threads & 31)) sh.threads = 256;
+    if (sh.threads_build < 32 || sh.threads_build > 256 || (sh.threads_build & 31)) sh.threads_build = 128;
+    cudaError_t e = raise_smem_attr(symbolic_kernel<T>, sh.smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, symbolic_kernel<T>, sh.threads_build, sh.smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)per_sm * h->sm_count;
+    const long long max_ctas = rows < kSymMaxCtas ? rows : kSymMaxCtas;
+    if (grid > max_ctas) grid = max_ctas;
+    if (grid < 1) grid = 1;
+    h->sym = sh;
+    h->sym_grid = (int)grid;
+    // the fast kernel stages a row's previous values and the hot part of its pool block in shared memory, two stages
+    // per warp.  Sized for 2.5x the mean block observed so far (the few longer rows are read from global memory), at
+    // most for the longest row the symbolic kernel stages, and shrunk until two CTAs fit an SM.
+    {
+        long long prods = sh.tmp_smem;
+        size_t hot = struct_layout<T>(sh.no_max, (int)prods).hot_bytes;
+        if (h->avg_hot > 0) {
+            size_t want = (size_t)(2.5 * (double)h->avg_hot);
+            if (want < 2048) want = 2048;
+            if (want < hot) hot = want;
+        }
+        FastShape f = fast_shape<T>(sh.no_max, (int)hot);
+        while (f.smem > (size_t)100 * 1024 && hot > 2048) {
+            hot = hot * 3 / 4;
+            f = fast_shape<T>(sh.no_max, (int)hot);
+        }
+        h->fast_no = 0;
+        if (f.smem + 1024 <= (size_t)h->max_smem_optin) {
+            e = raise_smem_attr(propagate_fast_kernel<T>, f.smem);
+            if (e != cudaSuccess) return (int)e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagate_fast_kernel<T>, kFastWarps * 32, f.smem);
+            if (e != cudaSuccess) return (int)e;
+            if (per_sm < 1) per_sm = 1;
+            h->fast_no = sh.no_max;
+            h->fshape = f;
+            h->fast_grid = per_sm * h->sm_count;
+            if (h->timeline)
+                fprintf(stderr, "shapes: fast no_max %d hot_max %d stage %zu smem %zu CTAs/SM %d (mean hot %lld) | symbolic H %d no_max %d km %d tmp_smem %d smem %zu grid %d\n",
+                        f.no_max, f.hot_max, f.stage, f.smem, per_sm, h->avg_hot, sh.H, sh.no_max, sh.km, sh.tmp_smem, sh.smem, h->sym_grid);
+        }
+    }
+    return 0;
 }
 
 // Sizes the row-group kernel: table / kept list per row from the caller's hints, lanes per row from the mean
@@ -385,30 +494,15 @@ int configure_group_shape(crwr_handle_s* h, long long max_row_len, long long max
     const size_t smem = sh.per_row * (size_t)w * (32 / g) + win_bytes;
     int per_sm = 0, e = 0;
     switch (g) {
-        case 4: e = group_kernel_attr<T, 4>(smem, w * 32, &per_sm); break;
-        case 8: e = group_kernel_attr<T, 8>(smem, w * 32, &per_sm); break;
-        case 16: e = group_kernel_attr<T, 16>(smem, w * 32, &per_sm); break;
-        default: e = group_kernel_attr<T, 32>(smem, w * 32, &per_sm); break;
+        case 4: e = group_kernel_attr<T, 4>(smem, w * 32, &per_sm, h->max_smem_optin); break;
+        case 8: e = group_kernel_attr<T, 8>(smem, w * 32, &per_sm, h->max_smem_optin); break;
+        case 16: e = group_kernel_attr<T, 16>(smem, w * 32, &per_sm, h->max_smem_optin); break;
+        default: e = group_kernel_attr<T, 32>(smem, w * 32, &per_sm, h->max_smem_optin); break;
     }
     if (e) return e;
     if (per_sm < 1) per_sm = 1;
     h->gshape = sh;
     h->ggrid = per_sm * h->sm_count;
-    // the fast kernel holds K+ and q of its rows in shared memory: as many operand slots per row as the row-group kernel
-    // accepts (a structure it built always fits), rows per warp by what a CTA may take
-    {
-        const int km = sh.kmax;
-        int rpw = 4;
-        while (rpw > 1 && fast_smem_bytes<T>(km, rpw) > (size_t)64 * 1024) rpw >>= 1;
-        const size_t fs = fast_smem_bytes<T>(km, rpw);
-        if (fs <= (size_t)h->max_smem_optin &&
-            cudaFuncSetAttribute(propagate_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs) == cudaSuccess) {
-            h->fast_km = km; h->fast_rpw = rpw; h->fast_smem = fs;
-        } else {
-            (void)cudaGetLastError();
-            h->fast_km = 0;         // rows this long stay on the row-group kernel
-        }
-    }
     return 0;
 }
 
@@ -466,8 +560,19 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     a.pool = h->at<unsigned char>(L.pool);
     a.pool_cap = (unsigned long long)L.pool_bytes;
     a.slow_list = h->at<int32_t>(L.slow_list);
-    a.build = 0;
     a.alpha = h->alpha;
+    a.fixed_base = L.fixed_base;
+    a.slot_cap = L.slot_cap;
+    a.sym_tmp = h->at<unsigned char>(L.sym_tmp);
+
+    {
+        // while many rows are built a warp reserves slot entries / pool bytes for about four rows at a time
+        long long sc = 4 * (long long)h->hint_len_eff;
+        if (sc < 256) sc = 256;
+        if (sc > 65536) sc = 65536;
+        a.slot_chunk = (int32_t)sc;
+        a.pool_chunk = (int32_t)(sc * 32 < (1 << 20) ? sc * 32 : (1 << 20));
+    }
     a.win_mode = 0;
     a.cand = nullptr;
     a.cand_cap = (unsigned long long)L.cand_cap;
@@ -488,19 +593,21 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
 }
 
 unsigned long long* cand_ptr(crwr_handle_s* h, int step);
+void tl_mark(crwr_handle_s* h, cudaStream_t st, const char* label);
 
-template <typename T, bool BUILD>
+template <typename T>
 void launch_group(const GroupShape& sh, bool pdl, int grid, size_t smem, cudaStream_t st, const PropArgs<T>& a) {
     switch (sh.G) {
-        case 4: launch_k(pdl, propagate_group_kernel<T, 4, BUILD>, grid, sh.warps * 32, smem, st, a, sh); break;
-        case 8: launch_k(pdl, propagate_group_kernel<T, 8, BUILD>, grid, sh.warps * 32, smem, st, a, sh); break;
-        case 16: launch_k(pdl, propagate_group_kernel<T, 16, BUILD>, grid, sh.warps * 32, smem, st, a, sh); break;
-        default: launch_k(pdl, propagate_group_kernel<T, 32, BUILD>, grid, sh.warps * 32, smem, st, a, sh); break;
+        case 4: launch_k(pdl, propagate_group_kernel<T, 4>, grid, sh.warps * 32, smem, st, a, sh); break;
+        case 8: launch_k(pdl, propagate_group_kernel<T, 8>, grid, sh.warps * 32, smem, st, a, sh); break;
+        case 16: launch_k(pdl, propagate_group_kernel<T, 16>, grid, sh.warps * 32, smem, st, a, sh); break;
+        default: launch_k(pdl, propagate_group_kernel<T, 32>, grid, sh.warps * 32, smem, st, a, sh); break;
     }
 }
 
-// The propagation of one walk step: [fast kernel: rows with a usable cached structure] -> row-group kernel (the rest;
-// records structures from kBuildStep on; warp-per-row kernel on step 0) -> [large-row kernel: deferred rows].
+// The propagation of one walk step.  Step 0: warp-per-row kernel (keeps scipy's storage order).  Steps before
+// build_step: row-group kernel.  From build_step on: [fast kernel: rows with a current cached structure] -> symbolic
+// kernel (the rest: structure build + numeric pass).  Behind either: [large-row kernel: deferred rows].
 // fused: the large-row kernel's last CTA scans the histograms (unsharded walk, histogram select).
 // win_step: the step's cut comes from the window select (tail.cuh): values are classified against the window.
 template <typename T>
@@ -520,38 +627,46 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, bool win_step, cu
     }
     const int rows = a.n_rows;
     const bool pdl = use_pdl(h);
-    const bool structs = h->structs_on && h->prop_kind == 1;
-    const bool use_fast = structs && step >= kFastStep && h->fast_km > 0;
-    a.build = (structs && step >= kBuildStep) ? 1 : 0;
+    const bool structs = h->structs_on && h->prop_kind == 1 && step >= h->build_step && h->fast_no > 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
         if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
         cudaEventRecord(e0, st);
     }
-    if (use_fast) {
-        const int R = kFastWarps * h->fast_rpw;
-        launch_k(pdl, propagate_fast_kernel<T>, (rows + R - 1) / R, kFastWarps * 32, h->fast_smem, st, a, h->fast_km, h->fast_rpw);
-        ++g_launches;
-        if (cudaGetLastError() != cudaSuccess) return -1;
-        // the row-group kernel walks the rows the fast kernel handed over
-        a.row_order = h->at<int32_t>(h->L.slow_list);
-        a.row_list_count = &h->at<WalkState>(h->L.state)->slow_count;
-    } else if (h->prop_kind == 1 && h->use_order && !h->order_valid && step >= kOrderStep && rows >= 64) {
-        // the walk has settled (the host sized the kernels from the third poll): rows by length, once
-        row_order_kernel<<<1, 1024, 0, st>>>(h->at<int32_t>(h->L.it_len[parity]), rows, h->at<int32_t>(h->L.row_order));
-        ++g_launches;
-        h->order_valid = true;
-        a.row_order = h->at<int32_t>(h->L.row_order);
-    }
-    if (h->prop_kind == 1 && step >= 1) {      // step 0 keeps scipy's storage order (warp-per-row kernel)
+    tl_mark(h, st, "step start");
+    if (structs) {
+        a.row_order = nullptr;
+        if (step > h->build_step) {
+            int grid = (rows + kFastWarps - 1) / kFastWarps;
+            if (grid > h->fast_grid) grid = h->fast_grid;
+            launch_k(pdl, propagate_fast_kernel<T>, grid, kFastWarps * 32, h->fshape.smem, st, a, h->fshape);
+            ++g_launches;
+            if (cudaGetLastError() != cudaSuccess) return -1;
+            tl_mark(h, st, "fast");
+            // the symbolic kernel walks the rows the fast kernel handed over
+            a.row_order = h->at<int32_t>(h->L.slow_list);
+            a.row_list_count = &h->at<WalkState>(h->L.state)->slow_count;
+        }
+        const SymShape& sh = h->sym;
+        int grid = rows < h->sym_grid ? rows : h->sym_grid;
+        // the first build has a row for every CTA (smaller CTAs, more rows in flight); later lists are short (larger
+        // CTAs, shorter latency per row)
+        launch_k(pdl, symbolic_kernel<T>, grid, step > h->build_step ? sh.threads : sh.threads_build, sh.smem, st, a, sh);
+    } else if (h->prop_kind == 1 && step >= 1) {      // step 0 keeps scipy's storage order (warp-per-row kernel)
+        if (h->use_order && !h->order_valid && step >= kOrderStep && rows >= 64) {
+            // the walk has settled (the host sized the kernels from the third poll): rows by length, once
+            row_order_kernel<<<1, 1024, 0, st>>>(h->at<int32_t>(h->L.it_len[parity]), rows, h->at<int32_t>(h->L.row_order));
+            ++g_launches;
+            h->order_valid = true;
+            a.row_order = h->at<int32_t>(h->L.row_order);
+        }
         const GroupShape& sh = h->gshape;
         const int rpc = sh.warps * (32 / sh.G);          // rows per CTA and pass
         int grid = (rows + rpc - 1) / rpc;
         if (grid > h->ggrid) grid = h->ggrid;
         if (grid < 1) grid = 1;
         const size_t smem = sh.per_row * (size_t)rpc + kHistWin * sizeof(unsigned int);
-        if (a.build) launch_group<T, true>(sh, pdl, grid, smem, st, a);
-        else launch_group<T, false>(sh, pdl, grid, smem, st, a);
+        launch_group<T>(sh, pdl, grid, smem, st, a);
     } else {
         const PropShape& sh = h->shape;
         int grid = (rows + sh.warps - 1) / sh.warps;
@@ -560,6 +675,7 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, bool win_step, cu
         launch_k(pdl, propagate_kernel<T>, grid, sh.warps * 32, sh.per_warp * (size_t)sh.warps + kHistWin * sizeof(unsigned int), st, a, sh);
     }
     ++g_launches;
+    tl_mark(h, st, "propagate/symbolic");
     if (h->profile) {
         cudaEventRecord(e1, st);
         h->ev.push_back(e0);
@@ -585,6 +701,7 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, bool win_step, cu
         launch_k(pdl, propagate_dense_kernel<T, kDenseWarpsPerCta>, (int)(L.dense_warps / kDenseWarpsPerCta), kDenseWarpsPerCta * 32, 0, st, a, sc);
         ++g_launches;
         if (cudaGetLastError() != cudaSuccess) return -1;
+        tl_mark(h, st, "large rows");
     }
     return 0;
 }
@@ -605,7 +722,7 @@ template <typename T>
 int launch_hist(crwr_handle_s* h, int out_parity, int level, int fused, cudaStream_t st) {
     const Layout& L = h->L;
     launch_k(use_pdl(h), select_hist_kernel<T>, h->sm_count, 512, 0, st, (const T*)h->at<T>(L.it_vals[out_parity]),
-             h->at<WalkState>(L.state), hist_ptr(h), level, fused);
+             L.fixed_base, h->at<WalkState>(L.state), hist_ptr(h), level, fused);
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -641,7 +758,7 @@ template <typename T>
 int launch_gather(crwr_handle_s* h, int out_parity, int fused, cudaStream_t st) {
     const Layout& L = h->L;
     launch_k(use_pdl(h), select_gather_kernel<T>, h->sm_count, 512, 0, st, (const T*)h->at<T>(L.it_vals[out_parity]),
-             h->at<WalkState>(L.state), cand_ptr(h, h->steps_enqueued), (unsigned long long)L.cand_cap, fused,
+             L.fixed_base, h->at<WalkState>(L.state), cand_ptr(h, h->steps_enqueued), (unsigned long long)L.cand_cap, fused,
              finish_args(h, 1, nullptr));
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -660,6 +777,7 @@ int launch_tail(crwr_handle_s* h, int out_parity, cudaStream_t st) {
     TailArgs a;
     a.fin = finish_args(h, 1, nullptr);
     a.vals = h->at<T>(L.it_vals[out_parity]);
+    a.fixed_base = L.fixed_base;
     a.cand = cand_ptr(h, h->steps_enqueued);
     a.cand_cap = (unsigned long long)L.cand_cap;
     launch_k(use_pdl(h), tail_kernel<T>, 1, 1024, 0, st, a);
@@ -679,6 +797,14 @@ DenseScratch<T> dense_scratch(crwr_handle_s* h) {
     sc.n = h->cfg.n_contigs;
     sc.words = L.words;
     return sc;
+}
+
+void tl_mark(crwr_handle_s* h, cudaStream_t st, const char* label) {
+    if (!h->profile || !h->timeline) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    h->tl.push_back(std::make_pair(e, label));
 }
 
 void prof_mark(crwr_handle_s* h, cudaStream_t st, int id) {
@@ -707,6 +833,7 @@ int enqueue_step(crwr_handle_s* h, cudaStream_t st) {
         prof_mark(h, st, 1);
         prof_mark(h, st, 2);
         if (launch_tail<T>(h, parity ^ 1, st)) return -1;
+        tl_mark(h, st, "tail");
         prof_mark(h, st, 3);
     } else {
         // propagate (+ level-0/1 histograms in its epilogue) -> large-row kernel (+ scans in its last CTA)
@@ -715,8 +842,10 @@ int enqueue_step(crwr_handle_s* h, cudaStream_t st) {
         if (launch_propagate<T>(h, parity, true, false, st)) return -1;
         prof_mark(h, st, 1);
         if (launch_hist<T>(h, parity ^ 1, 1, 1, st)) return -1;
+        tl_mark(h, st, "hist1");
         prof_mark(h, st, 2);
         if (launch_gather<T>(h, parity ^ 1, 1, st)) return -1;
+        tl_mark(h, st, "gather+finish");
         prof_mark(h, st, 3);
     }
     h->steps_enqueued = step + 1;
@@ -839,6 +968,7 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     // first crwr_walk_init (bitmaps_zeroed)
     int e = cfg->dtype == CRWR_F64 ? configure_shape<double>(h, 192, 32) : configure_shape<float>(h, 192, 32);
     if (!e) e = cfg->dtype == CRWR_F64 ? configure_group_shape<double>(h, 192, 32) : configure_group_shape<float>(h, 192, 32);
+    if (!e) e = cfg->dtype == CRWR_F64 ? configure_struct_shape<double>(h, 192, 32) : configure_struct_shape<float>(h, 192, 32);
     if (e) {
         release_pinned_state(h->h_state);
         delete h;
@@ -848,6 +978,9 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     if (const char* k = getenv("CRWR_PDL")) h->pdl_forced = atoi(k) != 0 ? 1 : 0;
     if (const char* k = getenv("CRWR_ROW_ORDER")) h->use_order = atoi(k) != 0;
     h->structs_on = env_int("CRWR_STRUCT", 1) != 0;
+    h->timeline = env_int("CRWR_TIMELINE", 0) != 0;
+    h->build_step = env_int("CRWR_BUILD_STEP", 2);
+    if (h->build_step < 2) h->build_step = 2;       // structures only exist behind a cut
     h->win_step = env_int("CRWR_WIN_STEP", 6);
     if (h->win_step > 0 && h->win_step < 2) h->win_step = 2;
     if (h->prop_kind != 1) h->win_step = 0;         // the warp-per-row kernel only knows the histogram select
@@ -923,6 +1056,7 @@ int32_t crwr_build_transition(crwr_handle h, const int64_t* d_indptr, const int3
     if (bad) CRWR_FAIL(CRWR_ERR_INVALID, "contact values must be finite and non-negative");
     h->p_nnz = total;
     h->have_p = true;
+
     if (h_nnz_out) *h_nnz_out = total;
     return CRWR_OK;
 }
@@ -940,6 +1074,7 @@ int32_t crwr_set_transition(crwr_handle h, const int32_t* d_indptr, const int32_
     CUDA_TRY(cudaMemcpyAsync(h->ws + L.p_vals, d_data, s * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
     h->p_nnz = nnz;
     h->have_p = true;
+
     return CRWR_OK;
 }
 
@@ -989,6 +1124,7 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     h->rp = rp;
     h->perc = perc;
     h->steps_enqueued = 0;
+    h->avg_hot = 0;
     h->fb_seen = false;
     h->dense_launched = true;
     h->order_valid = false;
@@ -1066,6 +1202,15 @@ int32_t crwr_profile_read(crwr_handle h, double* h_total_ms, int64_t* h_launches
         cudaEventDestroy(h->ev[i + 1]);
     }
     h->ev.clear();
+    for (size_t i = 0; i < h->tl.size(); ++i) {
+        float ms = 0.f;
+        if (i > 0 && strcmp(h->tl[i].second, "step start") != 0 &&
+            cudaEventElapsedTime(&ms, h->tl[i - 1].first, h->tl[i].first) == cudaSuccess)
+            fprintf(stderr, "  %-20s %8.1f us\n", h->tl[i].second, ms * 1e3);
+        else if (strcmp(h->tl[i].second, "step start") == 0) fprintf(stderr, "step\n");
+    }
+    for (auto& e : h->tl) cudaEventDestroy(e.first);
+    h->tl.clear();
     *h_total_ms = total;
     *h_launches = n;
     // step phases: [1] propagate + large-row kernel (+ scans), [2] level-1 histogram pass, [3] gather + finish
@@ -1091,7 +1236,8 @@ int32_t crwr_profile_phases(crwr_handle h, double* h_ms3) {
 
 int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept) {
     if (!h || max_row_len < 0 || max_kept < 0) CRWR_FAIL(CRWR_ERR_INVALID, "bad row hints");
-    if (max_row_len == h->hint_len && max_kept == h->hint_kept) return CRWR_OK;
+    if (max_row_len == h->hint_len && max_kept == h->hint_kept && !h->fast_retune) return CRWR_OK;
+    h->fast_retune = false;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     int e = h->cfg.dtype == CRWR_F64 ? configure_shape<double>(h, max_row_len, max_kept)
                                      : configure_shape<float>(h, max_row_len, max_kept);
@@ -1099,6 +1245,9 @@ int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept)
     e = h->cfg.dtype == CRWR_F64 ? configure_group_shape<double>(h, max_row_len, max_kept)
                                  : configure_group_shape<float>(h, max_row_len, max_kept);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "row-group kernel sizing failed: %s", cudaGetErrorString((cudaError_t)e));
+    e = h->cfg.dtype == CRWR_F64 ? configure_struct_shape<double>(h, max_row_len, max_kept)
+                                 : configure_struct_shape<float>(h, max_row_len, max_kept);
+    if (e) CRWR_FAIL(CRWR_ERR_CUDA, "symbolic kernel sizing failed: %s", cudaGetErrorString((cudaError_t)e));
     h->hint_len = max_row_len;
     h->hint_kept = max_kept;
     h->hint_len_eff = max_row_len;
@@ -1269,6 +1418,14 @@ int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
     // the host-side step counter follows the device: steps enqueued past the stop were skipped
     if (s.done) h->steps_enqueued = s.step;
     if (s.last_fallback_rows > 0) h->fb_seen = true;
+    if (s.hot_sum > 0) {
+        const long long rows = h->cfg.row_end - h->cfg.row_begin;
+        const long long avg = (long long)(s.hot_sum / (unsigned long long)(rows > 0 ? rows : 1));
+        if (h->avg_hot == 0 || avg > h->avg_hot + h->avg_hot / 4 || avg < h->avg_hot - h->avg_hot / 4) {
+            h->avg_hot = avg;
+            h->fast_retune = true;
+        }
+    }
     if (s.fb_unhandled) {
         h->dense_always = true;
         CRWR_FAIL(CRWR_ERR_RETRY, "rows were deferred in a step without a large-row kernel: walk again (the kernel is now always queued)");

@@ -119,8 +119,10 @@ struct WalkState {
     int32_t unordered_rows;            // the row-group kernel wrote this step's rows in slot-claim order (valid only behind a cut)
     // cached row structures (structure.cuh): rows whose kept set lies inside the cached superset take the fast kernel
     unsigned long long pool_cursor;    // bytes of the structure pool in use
-    unsigned int pool_gen;             // structures of an older generation are invalid (pool reset)
-    int32_t pool_reset_req;            // a build did not fit: the finish step resets the pool
+    unsigned long long slot_cursor;    // entries of the fixed-slot region (both iterate buffers) in use
+    unsigned long long hot_sum;        // bytes of the hot parts of all current structures (mod 2^64; the host sizes the fast kernel's stages)
+    unsigned int pool_gen;             // generation of this walk's structures (0 in a header = no structure)
+    int32_t struct_full;               // sticky: slot region or pool exhausted, later rows went without a structure
     unsigned int slow_count;           // rows the fast kernel handed to the row-group kernel this step
     unsigned int fast_rows;            // rows the fast kernel computed this step
     unsigned int built_rows;           // structures built this step
@@ -160,6 +162,12 @@ constexpr int kCandHeader = 2;
 struct Sq128 { unsigned long long lo, hi; };
 __device__ __forceinline__ void sq_add(Sq128& a, double x) {      // x >= 0
     if (!(x > 0.0)) return;
+    if (x < 1.0) {            // the usual case; same bits as the general path (integer part 0)
+        const unsigned long long f = __double2ull_rd(x * 18446744073709551616.0);
+        a.lo += f;
+        a.hi += (a.lo < f) ? 1ull : 0ull;
+        return;
+    }
     if (x >= 9.0e18) x = 9.0e18;
     const double h = floor(x);
     const unsigned long long f = __double2ull_rd((x - h) * 18446744073709551616.0);
@@ -192,10 +200,15 @@ __device__ __forceinline__ Sq128 sq_diff(const Sq128& pos, const Sq128& neg) {
 // Cached symbolic structure of one restart row (structure.cuh).
 struct RowStruct {
     long long off;          // byte offset of the row's block in the structure pool
-    int32_t nkp;            // |K+|: operand columns the structure covers
-    int32_t no;             // output columns
-    int32_t nprod;          // contributions (products)
-    uint32_t gen;           // pool generation the block belongs to; 0 = no structure
+    long long slot;         // the row's fixed slot: first entry in both iterate buffers (beyond the per-step region)
+    int32_t no;             // output columns (= entries of the slot)
+    int32_t nprod;          // products
+    int32_t nk;             // |K+|: operand columns the structure covers
+    int32_t dpos;           // position of the restart column among the outputs
+    uint32_t gen;           // walk generation the block belongs to; 0 = no structure
+    int32_t step;           // last walk step that wrote the row in structure order into its slot
+    int32_t hot_bytes;      // bytes of the block's hot part (what the fast kernel stages in shared memory)
+    int32_t pad;
 };
 
 template <typename T>

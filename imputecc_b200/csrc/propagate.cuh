@@ -47,8 +47,12 @@ struct PropArgs {
     unsigned char* pool;        // structure pool
     unsigned long long pool_cap;
     int32_t* slow_list;         // fast kernel: rows it could not take
-    int32_t build;              // row-group kernel: consume the superset K+ and record the row's structure
     float alpha;                // K+ = entries above alpha x cut
+    long long fixed_base;       // first entry of the fixed-slot region of both buffers (behind the out_cap per-step entries)
+    long long slot_cap;         // its entries
+    int32_t slot_chunk;         // symbolic kernel: entries / bytes a warp reserves at a time while many rows are built
+    int32_t pool_chunk;
+    unsigned char* sym_tmp;     // symbolic kernel: per-CTA staging regions (rows too long for shared-memory staging)
     int32_t win_mode;           // classify values against the select window when the walk state has one
     unsigned long long* cand;   // candidate block [count, successor, keys...] of the window select
     unsigned long long cand_cap;
@@ -881,6 +885,9 @@ __device__ __forceinline__ void dense_rows(const PropArgs<T>& a, const DenseScra
         // clear the bitmaps through the lists that set them
         for (int i = lane; i < count; i += 32) tbits[ord[i] >> 5] = 0u;
         for (int b = lane; b < len; b += 32) kbits[a.in.cols[ptr + b] >> 5] = 0u;
+        // an operand read from a fixed slot (structure.cuh) belongs to a row that has just lost its structure: the slot
+        // is abandoned and must not keep values for a later whole-array select pass
+        if (ptr >= a.fixed_base) for (int b = lane; b < len; b += 32) a.in.vals[ptr + b] = (T)0;
         __syncwarp();
     }
     totals_flush(a, wt);

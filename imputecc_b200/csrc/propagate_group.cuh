@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(1024) row_order_kernel(const int32_t* __restri
     }
 }
 
-template <typename T, int G, bool BUILD>
+template <typename T, int G>
 __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, GroupShape sh) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int RPW = 32 / G;                      // rows per warp
@@ -184,11 +184,6 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
     if (blockIdx.x == 0 && threadIdx.x == 0) a.st->unordered_rows = 1;
     const bool cut_on = __ldcg(&a.st->cut_on) != 0;
     const T cut = (T)__ldcg(&a.st->cut);
-    // build mode: the row is consumed through the superset K+ = {entries above alpha x cut}; members at or below
-    // the cut take q = 0 (exact-zero products change no bit), so the recorded structure also serves later steps
-    const bool build = BUILD && a.build != 0 && cut_on;
-    const T cut_lo = build ? (T)((double)a.alpha * (double)cut) : cut;
-    const unsigned pool_gen = __ldcg(&a.st->pool_gen);
     const bool win_mode = a.win_mode && __ldcg(&a.st->win_on) != 0;
     const unsigned long long wlo = __ldcg(&a.st->win_lo), whi = __ldcg(&a.st->win_hi);
     const int n_rows = a.row_list_count ? (int)__ldcg(a.row_list_count) : a.n_rows;
@@ -199,11 +194,14 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
 
     // per-lane totals: only the first lane of a group records its row; reduced over the warp at the end
     unsigned long long t_sq0 = 0, t_sq1 = 0, t_sq2 = 0, t_nnz = 0, t_kept = 0;
-    int t_max_kept = 0, t_max_len = 0, t_built = 0;
+    int t_max_kept = 0, t_max_len = 0;
 
     // Rows are handed out by an atomic counter.  (Measured and rejected: a static first pass - 9 % slower on long
     // rows, where neighbouring rows of one genome end up in one CTA - and asking for the next row at the start
     // of a pass - 7-10 % slower.)
+    // a slow list shorter than the grid: the surplus warps leave without touching the row counter (thousands of
+    // same-address atomics would otherwise cost more than the few listed rows)
+    if (a.row_list_count && (int)((blockIdx.x * (blockDim.x >> 5) + warp) * RPW) >= n_rows) goto rows_done;
     for (;;) {
         int r0 = 0;
         if (lane == 0) r0 = (int)atomicAdd(&a.st->row_counter, (unsigned)RPW);
@@ -223,7 +221,7 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
         const int maxlen = __reduce_max_sync(kFull, len);
         int32_t* ucol = cut_on ? kps : kcol;
         T* uval = cut_on ? tval : kval;
-        int nk = 0, nkt = 0;          // entries consumed (K+ in build mode) / truly kept (above the cut)
+        int nk = 0;                   // kept entries
         for (int b = 0; b < maxlen; b += 4 * G) {
             int32_t c[4];
             T v[4];
@@ -236,17 +234,15 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int e = b + u * G + sub;
-                const bool keep = (e < len) && (!cut_on || v[u] > cut_lo);
-                const bool kept_true = (e < len) && (!cut_on || v[u] > cut);
+                // a stored value is never zero: zeros are fixed-slot entries that count as absent (structure.cuh)
+                const bool keep = (e < len) && (cut_on ? v[u] > cut : v[u] != (T)0);
                 const unsigned m = __ballot_sync(kFull, keep) & gmask;
                 const int pos = nk + __popc(m & glt);
-                if (keep && pos < KMAX) { CRWR_CHECK(a.st, c[u] >= 0, 4); ucol[pos] = c[u]; uval[pos] = kept_true ? v[u] : (T)0; }
+                if (keep && pos < KMAX) { CRWR_CHECK(a.st, c[u] >= 0, 4); ucol[pos] = c[u]; uval[pos] = v[u]; }
                 nk += __popc(m);
-                if (build) nkt += __popc(__ballot_sync(kFull, kept_true) & gmask);
             }
         }
         __syncwarp();
-        if (!build) nkt = nk;
         t_max_kept = max(t_max_kept, nk);
         bool defer = nk > KMAX;
         int nk_live = (has_row && !defer) ? nk : 0;
@@ -428,9 +424,9 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
             t_sq2 += rowsq.hi;
             t_sq1 += rowsq.lo >> 32;
             t_sq0 += rowsq.lo & 0xffffffffull;
-            t_kept += (unsigned long long)nkt;
+            t_kept += (unsigned long long)nk;
             t_nnz += (unsigned long long)nz;
-            t_max_len = max(t_max_len, build ? n_cand : nz);      // build mode: the table also holds the outputs of K+ minus K
+            t_max_len = max(t_max_len, nz);
         }
 
         base = __shfl_sync(kFull, base, 0);
@@ -467,124 +463,10 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
             for (int i = written + sub; i < n_cand; i += G) { a.out.cols[base + i] = -1; a.out.vals[base + i] = (T)0; }
         }
         __syncwarp();
-        if (BUILD && build) {
-            // ---- record the row's structure (structure.cuh) while its table is still in place: output i = the i-th
-            // claimed slot (+ the restart column when it is a new column); for every output the products that feed
-            // it, in the order of the rounds above (= ascending k).  Two more walks over the row's products: count,
-            // then fill.  tval is free by now and hosts the slot -> output map and the per-output counters.
-            const int no = live ? cnt + (diag_new ? 1 : 0) : 0;
-            const int nkb = live ? nk : 0;
-            uint16_t* inv = reinterpret_cast<uint16_t*>(tval);
-            uint16_t* ccnt = inv + H;
-            for (int i = sub; i < cnt; i += G) inv[ord[i]] = (uint16_t)i;
-            for (int i = sub; i < no; i += G) ccnt[i] = 0;
-            __syncwarp();
-            const int maxnkb = __reduce_max_sync(kFull, nkb);
-            for (int idx = 0; idx < maxnkb; ++idx) {
-                const bool has = idx < nkb;
-                const int ps = has ? kps[idx] : 0, ln = has ? klen[idx] : 0;
-                const int maxln = __reduce_max_sync(kFull, ln);
-                for (int e0 = 0; e0 < maxln; e0 += G) {
-                    const int e = e0 + sub;
-                    if (e < ln) { const int slot = lookup(__ldg(pcols + ps + e)); CRWR_CHECK(a.st, slot >= 0, 7); if (slot >= 0) ccnt[inv[slot]] += 1; }
-                    __syncwarp();
-                }
-            }
-            int nprod = 0;
-            for (int i = sub; i < no; i += G) nprod += ccnt[i];
-#pragma unroll
-            for (int o = G >> 1; o > 0; o >>= 1) nprod += __shfl_xor_sync(kFull, nprod, o);
-            // one reservation of the pool per warp
-            unsigned long long myb = (live && no > 0 && nprod <= 65535 && no <= 65535) ? (unsigned long long)struct_bytes<T>(nkb, no, nprod) : 0ull;
-            unsigned long long offs_b = 0, total_b = 0;
-#pragma unroll
-            for (int g = 0; g < RPW; ++g) {
-                const unsigned long long v = __shfl_sync(kFull, myb, g * G);
-                if (g < grp) offs_b += v;
-                total_b += v;
-            }
-            unsigned long long pbase = 0;
-            if (lane == 0 && total_b) pbase = atomicAdd(&a.st->pool_cursor, total_b);
-            pbase = __shfl_sync(kFull, pbase, 0);
-            const bool pfit = pbase + total_b <= a.pool_cap;
-            if (!pfit && lane == 0 && total_b) a.st->pool_reset_req = 1;
-            const bool doit = myb != 0ull && pfit;
-            unsigned char* blk = a.pool + pbase + offs_b;
-            const StructView<T> sv = struct_view<T>(blk, nkb, no, nprod);
-            int32_t* kcols_w = const_cast<int32_t*>(sv.kcols);
-            uint32_t* kmask_w = const_cast<uint32_t*>(sv.kmask);
-            int32_t* ocols_w = const_cast<int32_t*>(sv.ocols);
-            int32_t* cptr_w = const_cast<int32_t*>(sv.cptr);
-            uint16_t* okidx_w = const_cast<uint16_t*>(sv.okidx);
-            uint16_t* ckidx_w = const_cast<uint16_t*>(sv.ckidx);
-            T* cw_w = const_cast<T*>(sv.cw);
-            // exclusive scan of the counters -> cptr; the counters then serve as fill cursors
-            const int maxno = __reduce_max_sync(kFull, no);
-            int run = 0;
-            for (int b = 0; b < maxno; b += G) {
-                const int i = b + sub;
-                const int c = i < no ? (int)ccnt[i] : 0;
-                int incl = c;
-#pragma unroll
-                for (int o = 1; o < G; o <<= 1) {
-                    const int v = __shfl_up_sync(kFull, incl, o, G);
-                    if (sub >= o) incl += v;
-                }
-                const int excl = run + incl - c;
-                if (i < no) {
-                    ccnt[i] = (uint16_t)excl;
-                    if (doit) cptr_w[i] = excl;
-                }
-                run += __shfl_sync(kFull, incl, grp * G + G - 1);
-            }
-            if (doit) {
-                if (sub == 0) cptr_w[no] = run;
-                for (int i = sub; i < no; i += G) { okidx_w[i] = (uint16_t)0xFFFF; ocols_w[i] = i < cnt ? tkey[ord[i]] : dcol; }
-                for (int i = sub; i < ((nkb + 31) >> 5); i += G) kmask_w[i] = 0u;
-                for (int i = sub; i < nkb; i += G) kcols_w[i] = kcol[i];
-            }
-            __syncwarp();
-            if (doit) {
-                // operand columns that are output columns too: their old value enters the norm against the new one
-                for (int k = sub; k < nkb; k += G) {
-                    const int32_t j = kcol[k];
-                    const int slot = lookup(j);
-                    int oi = -1;
-                    if (slot >= 0) oi = (int)inv[slot];
-                    else if (j == dcol && diag_new) oi = cnt;
-                    if (oi >= 0) { okidx_w[oi] = (uint16_t)k; atomicOr(&kmask_w[k >> 5], 1u << (k & 31)); }
-                }
-            }
-            for (int idx = 0; idx < maxnkb; ++idx) {
-                const bool has = idx < nkb;
-                const int ps = has ? kps[idx] : 0, ln = has ? klen[idx] : 0;
-                const int maxln = __reduce_max_sync(kFull, ln);
-                for (int e0 = 0; e0 < maxln; e0 += G) {
-                    const int e = e0 + sub;
-                    if (doit && e < ln) {
-                        const int slot = lookup(__ldg(pcols + ps + e));
-                        if (slot >= 0) {
-                            const int oi = (int)inv[slot];
-                            const int pos_ = (int)ccnt[oi];
-                            ccnt[oi] = (uint16_t)(pos_ + 1);
-                            ckidx_w[pos_] = (uint16_t)idx;
-                            cw_w[pos_] = __ldg(pvals + ps + e);
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            if (doit && sub == 0) {
-                RowStruct hdr;
-                hdr.off = (long long)(pbase + offs_b); hdr.nkp = nkb; hdr.no = no; hdr.nprod = nprod; hdr.gen = pool_gen;
-                a.rs[row] = hdr;
-                t_built += 1;
-            }
-            __syncwarp();
-        }
         for (int i = sub; i < cnt; i += G) tkey[ord[i]] = -1;
         __syncwarp();
     }
+rows_done:
     pdl_launch_dependents();        // this warp is out of rows: the next kernel's CTAs may take the SM as it empties
 
     // ---- publish the warp's totals
@@ -598,8 +480,6 @@ __global__ void __launch_bounds__(256) propagate_group_kernel(PropArgs<T> a, Gro
     }
     t_max_kept = __reduce_max_sync(kFull, t_max_kept);
     t_max_len = __reduce_max_sync(kFull, t_max_len);
-    t_built = __reduce_add_sync(kFull, t_built);
-    if (BUILD && lane == 0 && t_built) atomicAdd(&a.st->built_rows, (unsigned)t_built);
     // one set of global atomics per CTA: the warps meet in shared memory first
     __shared__ unsigned long long s_tot[5];
     __shared__ int s_max[2];

@@ -353,8 +353,6 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
         }
         // deferred rows with no large-row kernel behind the propagation: the step is incomplete, the host retries
         if (fb > 0 && !a.dense_launched) st->fb_unhandled = 1;
-        // a structure build did not fit the pool: start a new generation (every row rebuilds on its next slow pass)
-        if (st->pool_reset_req) { st->pool_cursor = 0; st->pool_gen += 1; st->pool_reset_req = 0; }
         // select window of the next step: the cut moves less and less, so it will lie within a few times its last move
         {
             int on = 0;
@@ -434,9 +432,28 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
 // One histogram pass over the value array by the whole grid: level 0 counts the top 12 key bits of every
 // value, level 1 the next 12 bits of the values inside level-0 bin `prefix`.  `sh` is a 4096-bin
 // shared-memory histogram private to the CTA; it is flushed with one atomic per non-empty bin.
+// The value array of a step is two ranges: [0, n) the per-step region, [fixed_base, fixed_base + n_fixed) the fixed slots
+// of rows with a cached structure (structure.cuh); entry i >= n of the concatenation lives at fixed_base + (i - n).
+struct ValRanges { long long n, fixed_base, n_fixed; };
+__device__ __forceinline__ ValRanges val_ranges(const WalkState* st, long long fixed_base) {
+    ValRanges r;
+    r.n = (long long)st->cursor;
+    r.fixed_base = fixed_base;
+    r.n_fixed = (long long)st->slot_cursor;
+    if (r.n_fixed > fixed_base - 16) r.n_fixed = fixed_base - 16;   // the fixed region is at least as long as that (api.cu, make_layout)
+    return r;
+}
 template <typename T>
-__device__ __forceinline__ void hist_pass(const T* __restrict__ vals, long long n, typename KeyOf<T>::type prefix, int level,
+__device__ __forceinline__ T range_load(const T* __restrict__ vals, const ValRanges& r, long long i) {
+    if (i < r.n) return vals[i];
+    if (i < r.n + r.n_fixed) return vals[r.fixed_base + (i - r.n)];
+    return (T)0;
+}
+
+template <typename T>
+__device__ __forceinline__ void hist_pass(const T* __restrict__ vals, const ValRanges rg, typename KeyOf<T>::type prefix, int level,
                                           unsigned int* sh, unsigned long long* hist) {
+    const long long n = rg.n + rg.n_fixed;
     typedef KeyOf<T> KO;
     typedef typename KO::type K;
     for (int i = threadIdx.x; i < kSelectBins; i += blockDim.x) sh[i] = 0u;
@@ -445,7 +462,7 @@ __device__ __forceinline__ void hist_pass(const T* __restrict__ vals, long long 
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
         T vv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const long long i = i0 + u * stride; vv[u] = i < n ? vals[i] : (T)0; }
+        for (int u = 0; u < 4; ++u) vv[u] = range_load(vals, rg, i0 + u * stride);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const T v = vv[u];
@@ -468,14 +485,14 @@ __device__ __forceinline__ void hist_pass(const T* __restrict__ vals, long long 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512) select_hist_kernel(const T* vals, WalkState* st, unsigned long long* __restrict__ hist,
-                                                          int level, int fused_tail) {
+__global__ void __launch_bounds__(512) select_hist_kernel(const T* vals, long long fixed_base, WalkState* st,
+                                                          unsigned long long* __restrict__ hist, int level, int fused_tail) {
     __shared__ unsigned int sh[kSelectBins];
     pdl_wait();
     pdl_launch_dependents();
     if (st->done) return;
     if (level == 1 && st->hist1_ready) return;      // the propagate epilogue already filled this level and it was scanned
-    hist_pass<T>(vals, (long long)st->cursor, (typename KeyOf<T>::type)st->prefix, level, sh, hist);
+    hist_pass<T>(vals, val_ranges(st, fixed_base), (typename KeyOf<T>::type)st->prefix, level, sh, hist);
     if (fused_tail && last_block(&st->tick_hist1)) scan_level<T, 512>(st, hist, level);
 }
 
@@ -489,17 +506,18 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(WalkState* st, const 
 // Candidate block layout (uint64): [0] count, [1] smallest key above the candidate bin, [2..] keys.
 // One pass over the value array by the whole grid.
 template <typename T>
-__device__ __forceinline__ void gather_pass(const T* __restrict__ vals, long long n, typename KeyOf<T>::type prefix,
+__device__ __forceinline__ void gather_pass(const T* __restrict__ vals, const ValRanges rg, typename KeyOf<T>::type prefix,
                                             unsigned long long* block, unsigned long long cand_cap) {
     typedef KeyOf<T> KO;
     typedef typename KO::type K;
+    const long long n = rg.n + rg.n_fixed;
     const long long stride = (long long)gridDim.x * blockDim.x;
     K best = ~(K)0;
     bool have = false;
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
         T vv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const long long i = i0 + u * stride; vv[u] = i < n ? vals[i] : (T)0; }
+        for (int u = 0; u < 4; ++u) vv[u] = range_load(vals, rg, i0 + u * stride);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const T v = vv[u];
@@ -522,13 +540,14 @@ __device__ __forceinline__ void gather_pass(const T* __restrict__ vals, long lon
 
 // fused (unsharded walks): the last CTA to finish runs the step's finish logic.
 template <typename T>
-__global__ void __launch_bounds__(512) select_gather_kernel(const T* vals, WalkState* st, unsigned long long* __restrict__ block,
-                                                            unsigned long long cand_cap, int fused, FinishArgs fin) {
+__global__ void __launch_bounds__(512) select_gather_kernel(const T* vals, long long fixed_base, WalkState* st,
+                                                            unsigned long long* __restrict__ block, unsigned long long cand_cap,
+                                                            int fused, FinishArgs fin) {
     __shared__ __align__(16) unsigned char scratch[kFinishScratchBytes];
     pdl_wait();
     pdl_launch_dependents();
     if (st->done) return;
-    gather_pass<T>(vals, (long long)st->cursor, (typename KeyOf<T>::type)st->prefix, block, cand_cap);
+    gather_pass<T>(vals, val_ranges(st, fixed_base), (typename KeyOf<T>::type)st->prefix, block, cand_cap);
     if (fused && last_block(&st->tick_gather)) finish_step_body<T>(fin, scratch);
 }
 

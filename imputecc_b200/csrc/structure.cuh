@@ -1,268 +1,167 @@
-// K2, cached-structure form: the walk step's propagation (utility.py:282-283 fused with the lazy cut of
-// utility.py:290) for rows whose SYMBOLIC work is already known.
+// K2, symbolic / numeric form: the walk step's propagation (utility.py:282-283 fused with the lazy cut of
+// utility.py:290) split the way sparse products are split when the same pattern is multiplied again and again.
 //
 // From the third walk step on the kept set of a restart row barely moves (the walk plateaus),
-// yet the row-group kernel redoes the whole symbolic part of the row's SpGEMM every step: hashing, slot claims,
-// first-touch lists.  Here the symbolic result is cached per row, once, for a SUPERSET K+ of the kept columns
-// (the row's entries above alpha x cut, alpha < 1):
-//     K+            the operand columns, ascending          O             the output columns they reach (+ restart column)
-//     per output    its contributions (index into K+, P value) in ascending k = exactly scipy's summation order
-// A later step may use the structure whenever its kept set is INSIDE K+: members of K+ at or below the cut take
-// q = 0, their products are exact zeros and adding them changes no bit; outputs reached only through them come
-// out 0 and are dropped like csr_matmat drops them.  The numeric pass is then output-stationary: one lane per
-// output column adds that column's products in order (separate multiply and add, as everywhere) - no hash
-// table, no atomics, no shared-memory read-modify-write chain, no synchronisation inside a row.
+// yet a hash-accumulating kernel redoes the whole symbolic part of the row's SpGEMM every step.  Here the
+// symbolic result is computed ONCE per row (symbolic_kernel) for a SUPERSET K+ of the kept columns (the row's
+// entries above alpha x cut, alpha < 1) and cached in a pool:
+//     O             the output columns K+ reaches, plus K+ itself and the restart column, sorted by the number
+//                   of products that feed them (descending) - this is also the row's STORAGE ORDER from now on
+//     per output    its products (position of the operand in O, P value) in ascending operand column = exactly
+//                   scipy's summation order; the lists of the 32 outputs of a block are interleaved round by
+//                   round (round j holds the j-th product of every output that has one), so a warp reads them
+//                   with fully coalesced loads and no padding
+// and the row gets a FIXED slot of |O| entries in both iterate buffers.  A later step may use the structure
+// whenever its kept set is INSIDE K+ (one bit per output): members of K+ at or below the cut take q = 0, their
+// products are exact zeros and adding them changes no bit; outputs reached only through them come out 0 and
+// count as absent, like csr_matmat drops them.  The numeric pass (numeric_row) is then output-stationary: one
+// lane per output adds that output's products in order (separate multiply and add, as everywhere) - no hash
+// table, no atomics, no sorting, no allocation, and the previous value of the same output (for ||Q - Q~||) sits
+// at the same position of the input row.
 //
-// Rows whose kept set left K+ (or that have no structure yet) are appended to a list that the row-group kernel
-// of the same step walks; it rebuilds their structures (build_row_structures below).
+// fast_kernel       rows with a current structure: validate (kept set inside K+), numeric pass; others -> slow list
+// symbolic_kernel   rows of the slow list (all rows on the first structure step): build the structure, numeric pass
+// Rows that exceed the symbolic kernel's tables go to the large-row kernel (fb_rows) and keep no structure.
 #pragma once
 #include "propagate.cuh"
 
 namespace crwr {
 
-constexpr int kFastWarps = 4;              // warps per CTA of the fast kernel
+constexpr int kFastWarps = 4;               // warps per CTA of the fast kernel
+constexpr int kSymMaxCtas = 148 * 8;         // CTAs of one symbolic_kernel launch (each owns a global staging region)
 
-// Pool block of one row: [kcols nkp x i32][kmask ceil(nkp/32) x u32][ocols no x i32][cptr (no+1) x i32]
-//                        [okidx no x u16][ckidx nprod x u16](pad to 8)[cw nprod x T]
+// Pool block of one row, nb = ceil(no / 32).  The part the numeric pass reads comes first, 16-byte aligned and a
+// multiple of 16 bytes long, so that one bulk copy (TMA) brings it into shared memory:
+//   [bptr (nb+1) x i32][kbits nb x u32][cnt no x u16](pad 4)[ck nprod x u16](pad 16)[cw nprod x T](pad 16) | [ocols no x i32]
+struct StructLayout { size_t ocols, bptr, kbits, cnt, ck, cw, hot_bytes, bytes; };
 template <typename T>
-struct StructView {
-    const int32_t* kcols;
-    const uint32_t* kmask;
-    const int32_t* ocols;
-    const int32_t* cptr;
-    const uint16_t* okidx;
-    const uint16_t* ckidx;
-    const T* cw;
-};
-__host__ __device__ inline size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
-template <typename T>
-__host__ __device__ inline size_t struct_bytes(int nkp, int no, int nprod) {
-    size_t b = 4 * (size_t)nkp + 4 * (size_t)((nkp + 31) >> 5) + 4 * (size_t)no + 4 * (size_t)(no + 1) + 2 * (size_t)no + 2 * (size_t)nprod;
-    return align8(b) + align8(sizeof(T) * (size_t)nprod);
-}
-template <typename T>
-__device__ __forceinline__ StructView<T> struct_view(const unsigned char* p, int nkp, int no, int nprod) {
-    StructView<T> v;
-    v.kcols = reinterpret_cast<const int32_t*>(p);   p += 4 * (size_t)nkp;
-    v.kmask = reinterpret_cast<const uint32_t*>(p);  p += 4 * (size_t)((nkp + 31) >> 5);
-    v.ocols = reinterpret_cast<const int32_t*>(p);   p += 4 * (size_t)no;
-    v.cptr = reinterpret_cast<const int32_t*>(p);    p += 4 * (size_t)(no + 1);
-    v.okidx = reinterpret_cast<const uint16_t*>(p);  p += 2 * (size_t)no;
-    v.ckidx = reinterpret_cast<const uint16_t*>(p);  p += 2 * (size_t)nprod;
-    const size_t head = 4 * (size_t)nkp + 4 * (size_t)((nkp + 31) >> 5) + 4 * (size_t)no + 4 * (size_t)(no + 1) + 2 * (size_t)no + 2 * (size_t)nprod;
-    p += align8(head) - head;
-    v.cw = reinterpret_cast<const T*>(p);
-    return v;
+__host__ __device__ inline StructLayout struct_layout(int no, int nprod) {
+    const size_t nb = (size_t)((no + 31) >> 5);
+    StructLayout L;
+    size_t o = 0;
+    L.bptr = o;  o += 4 * (nb + 1);
+    L.kbits = o; o += 4 * nb;
+    L.cnt = o;   o += 2 * (size_t)no;
+    o = (o + 3) & ~(size_t)3;
+    L.ck = o;    o += 2 * (size_t)nprod;
+    o = (o + 15) & ~(size_t)15;
+    L.cw = o;    o += sizeof(T) * (size_t)nprod;
+    o = (o + 15) & ~(size_t)15;
+    L.hot_bytes = o;
+    L.ocols = o; o += 4 * (size_t)no;
+    L.bytes = (o + 15) & ~(size_t)15;
+    return L;
 }
 
-// ---------------------------------------------------------------------------------------------
-// The fast kernel.  CTA b owns the R = kFastWarps * rpw consecutive rows starting at b * R (static schedule):
-//   A  validate: header present and current, then every kept entry of the operand row must be a member of K+
-//      (binary search in the shared-memory copy of K+); q[] receives the kept values, 0 elsewhere
-//   -  one reservation of the product buffer and one append to the slow list per CTA
-//   B  per valid row: out[s] = sum of its contributions in order, scale, restart, norm terms, selection
-//      bookkeeping (histogram or window), compacted write
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__host__ __device__ inline size_t fast_smem_bytes(int km, int rpw) {
-    const size_t R = (size_t)kFastWarps * rpw;
-    return align16(R * km * 4) + align16(R * km * sizeof(T)) + align16(R * sizeof(RowStruct)) + align16(R * 8) + 2 * align16(R * 4) +
-           align16((size_t)kHistWin * 4) + 64;
+// ---- bulk asynchronous copies global -> shared (TMA, cp.async.bulk) completing on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// Where a step's values go for the percentile select: histogram (early steps, sharded walks) or window (propagate.cuh,
+// win_classify - restated here with keys of the data's own width and a 32-bit counter per lane).
 template <typename T>
-__global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArgs<T> a, int KM, int RPW) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int R = kFastWarps * RPW;
-    const int lane = lane_id();
-    const int warp = threadIdx.x >> 5;
-    unsigned char* p = smem_raw;
-    int32_t* s_kc = reinterpret_cast<int32_t*>(p);       p += align16((size_t)R * KM * 4);
-    T* s_qk = reinterpret_cast<T*>(p);                   p += align16((size_t)R * KM * sizeof(T));
-    RowStruct* s_hdr = reinterpret_cast<RowStruct*>(p);  p += align16((size_t)R * sizeof(RowStruct));
-    long long* s_base = reinterpret_cast<long long*>(p); p += align16((size_t)R * 8);
-    int* s_ok = reinterpret_cast<int*>(p);               p += align16((size_t)R * 4);
-    int* s_nk = reinterpret_cast<int*>(p);               p += align16((size_t)R * 4);
-    unsigned int* win = reinterpret_cast<unsigned int*>(p); p += align16((size_t)kHistWin * 4);
-    unsigned int* s_wn = reinterpret_cast<unsigned int*>(p);
-    int* s_fits = reinterpret_cast<int*>(p + 4);
-
-    for (int i = threadIdx.x; i < kHistWin; i += blockDim.x) win[i] = 0u;
-    if (threadIdx.x == 0) { *s_wn = 0u; *s_fits = 1; }
-    pdl_wait();
-    WalkState* st = a.st;
-    if (st->done) return;
-    const bool cut_on = __ldcg(&st->cut_on) != 0;
-    const T cut = (T)__ldcg(&st->cut);
-    const unsigned gen = __ldcg(&st->pool_gen);
-    const bool win_mode = a.win_mode && __ldcg(&st->win_on) != 0;
-    const unsigned long long wlo = __ldcg(&st->win_lo), whi = __ldcg(&st->win_hi);
-    const bool pred_valid = a.prefill_l1 && __ldcg(&st->pred_valid) != 0;
-    const typename KeyOf<T>::type pred0 = (typename KeyOf<T>::type)__ldcg(&st->pred_prefix0);
-    const WinStage stage = {reinterpret_cast<unsigned long long*>(win), s_wn};
-    WinAcc wacc = {0ull, ~0ull};
-
-    const int row0 = blockIdx.x * R;
-    const int nrows = min(R, a.n_rows - row0);
-
-    // ---- A0: headers
-    if ((int)threadIdx.x < R) {
-        const int r = threadIdx.x;
-        RowStruct h = {0, 0, 0, 0, 0u};
-        if (r < nrows) h = a.rs[row0 + r];
-        s_hdr[r] = h;
-        s_ok[r] = (r < nrows && cut_on && h.gen == gen && gen != 0u && h.nkp <= KM) ? 1 : 0;
-        s_nk[r] = 0;
-    }
-    __syncthreads();
-
-    // ---- A1: membership of the kept entries in K+, q values
-    for (int i = 0; i < RPW; ++i) {
-        const int r = warp * RPW + i;
-        if (r >= nrows || !s_ok[r]) continue;
-        const RowStruct h = s_hdr[r];
-        const int row = row0 + r;
-        const int32_t* kcols = reinterpret_cast<const int32_t*>(a.pool + h.off);
-        int32_t* kc = s_kc + (size_t)r * KM;
-        T* qk = s_qk + (size_t)r * KM;
-        for (int k = lane; k < h.nkp; k += 32) { kc[k] = __ldg(kcols + k); qk[k] = (T)0; }
-        __syncwarp();
-        const long long ptr = a.in.row_ptr[row];
-        const int len = a.in.row_len[row];
-        const int32_t* rc = a.in.cols + ptr;
-        const T* rv = a.in.vals + ptr;
-        bool bad = false;
-        int nkept = 0;
-        for (int b = 0; b < len; b += 32) {
-            const int e = b + lane;
-            bool keep = false;
-            T v = (T)0;
-            if (e < len) { v = __ldg(rv + e); keep = v > cut; }
-            if (keep) {
-                const int32_t c = __ldg(rc + e);
-                int lo = 0, hi = h.nkp;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (kc[mid] < c) lo = mid + 1; else hi = mid;
+struct SelCtx {
+    typedef typename KeyOf<T>::type K;
+    bool win_mode, pred_valid;
+    K klo, khi, succ;
+    unsigned int below;
+    K pred0;
+    unsigned long long* hist;
+    unsigned int* win;
+    WinStage stage;
+    unsigned long long* cand;
+    unsigned long long cand_cap;
+    __device__ __forceinline__ void add(bool nzv, T v) {          // all 32 lanes of the warp
+        if (win_mode) {
+            if (nzv) {
+                const K key = KeyOf<T>::enc(v);
+                if (key < klo) below += 1u;
+                else if (key >= khi) succ = key < succ ? key : succ;
+                else {
+                    const unsigned int pos = atomicAdd(stage.count, 1u);
+                    if (pos < (unsigned)kWinStage) stage.keys[pos] = (unsigned long long)key;
+                    else {
+                        const unsigned long long idx = atomicAdd(&cand[0], 1ull);
+                        if (idx < cand_cap) cand[kCandHeader + idx] = (unsigned long long)key;
+                    }
                 }
-                if (lo < h.nkp && kc[lo] == c) qk[lo] = v; else bad = true;
             }
-            nkept += __popc(__ballot_sync(kFull, keep));
-        }
-        bad = __any_sync(kFull, bad);
-        if (lane == 0) { s_ok[r] = bad ? 0 : 1; s_nk[r] = nkept; }
+        } else if (hist) hist_values<T>(hist, win, nzv, v, pred_valid, pred0);
     }
-    __syncthreads();
-
-    // ---- one reservation of the product buffer, one append to the slow list
-    if (warp == 0) {
-        const int r = lane;
-        const bool ok = r < nrows && s_ok[r] != 0;
-        const bool inv = r < nrows && s_ok[r] == 0;
-        const int no = ok ? s_hdr[r].no : 0;
-        int incl = no;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(kFull, incl, 31);
-        long long base = 0;
-        if (lane == 0 && total > 0) base = (long long)atomicAdd(&st->cursor, (unsigned long long)total);
-        base = __shfl_sync(kFull, base, 0);
-        if (r < R) s_base[r] = base + incl - no;
-        if (lane == 0 && base + total > a.out_cap) { st->capacity_overflow = 1; *s_fits = 0; }
-        const unsigned im = __ballot_sync(kFull, inv);
-        const unsigned om = __ballot_sync(kFull, ok);
-        if (im) {
-            unsigned sb = 0;
-            if (lane == 0) sb = atomicAdd(&st->slow_count, (unsigned)__popc(im));
-            sb = __shfl_sync(kFull, sb, 0);
-            if (inv) a.slow_list[sb + __popc(im & lanemask_lt())] = row0 + r;
-        }
-        if (lane == 0 && om) atomicAdd(&st->fast_rows, (unsigned)__popc(om));
+    __device__ __forceinline__ void flush(WalkState* st) {        // CTA-wide
+        if (win_mode) {
+            WinAcc w;
+            w.below = (unsigned long long)below;
+            w.succ = succ == ~(K)0 ? ~0ull : (unsigned long long)succ;
+            win_flush(w, stage, cand, cand_cap, st);
+        } else if (hist) hist_window_flush<T>(hist, win);
     }
-    __syncthreads();
-    const bool fits = *s_fits != 0;
+};
+template <typename T>
+__device__ __forceinline__ SelCtx<T> make_sel(const PropArgs<T>& a, unsigned int* win, unsigned int* win_count) {
+    typedef typename KeyOf<T>::type K;
+    SelCtx<T> s;
+    WalkState* st = a.st;
+    s.win_mode = a.win_mode && __ldcg(&st->win_on) != 0;
+    s.klo = (K)__ldcg(&st->win_lo);
+    s.khi = (K)__ldcg(&st->win_hi);
+    s.succ = ~(K)0;
+    s.below = 0u;
+    s.pred_valid = a.prefill_l1 && __ldcg(&st->pred_valid) != 0;
+    s.pred0 = (K)__ldcg(&st->pred_prefix0);
+    s.hist = a.hist;
+    s.win = win;
+    s.stage.keys = reinterpret_cast<unsigned long long*>(win);
+    s.stage.count = win_count;
+    s.cand = a.cand;
+    s.cand_cap = a.cand_cap;
+    return s;
+}
 
-    // ---- B: numeric pass
-    unsigned long long t_sq0 = 0, t_sq1 = 0, t_sq2 = 0, t_nnz = 0, t_kept = 0;
-    int t_max_kept = 0, t_max_len = 0;
-    for (int i = 0; i < RPW; ++i) {
-        const int r = warp * RPW + i;
-        if (r >= nrows || !s_ok[r]) continue;
-        const RowStruct h = s_hdr[r];
-        const int row = row0 + r;
-        const StructView<T> sv = struct_view<T>(a.pool + h.off, h.nkp, h.no, h.nprod);
-        const T* qk = s_qk + (size_t)r * KM;
-        const int32_t dcol = a.row_begin + row;
-        const long long base = s_base[r];
-        Sq128 pos = {0ull, 0ull};
-        int written = 0;
-        for (int b = 0; b < h.no; b += 32) {
-            const int s = b + lane;
-            const bool act = s < h.no;
-            T v = (T)0;
-            int32_t col = -1;
-            if (act) {
-                const int cb = __ldg(sv.cptr + s), ce = __ldg(sv.cptr + s + 1);
-                T acc = (T)0;
-                for (int c = cb; c < ce; ++c) acc = add_rn(acc, mul_rn(qk[__ldg(sv.ckidx + c)], __ldg(sv.cw + c)));
-                v = mul_rn(a.scale, acc);
-                col = __ldg(sv.ocols + s);
-                if (col == dcol) v = add_rn(v, a.restart);
-                const unsigned ok_ = __ldg(sv.okidx + s);
-                const T old = ok_ != 0xFFFFu ? qk[ok_] : (T)0;
-                if (old != (T)0) { const T d = sub_rn(old, v); sq_add(pos, (double)d * (double)d); }
-                else sq_add(pos, (double)v * (double)v);
-            }
-            const bool nzv = act && v != (T)0;
-            if (win_mode) win_classify<T>(nzv, v, wlo, whi, wacc, stage, a.cand, a.cand_cap);
-            else if (a.hist) hist_values<T>(a.hist, win, nzv, v, pred_valid, pred0);
-            const unsigned m = __ballot_sync(kFull, nzv);
-            if (nzv && fits) {
-                const long long o = base + written + __popc(m & lanemask_lt());
-                CRWR_CHECK(st, o >= 0 && o < a.out_cap, 6);
-                a.out.cols[o] = col;
-                a.out.vals[o] = v;
-            }
-            written += __popc(m);
-        }
-        // kept operand columns that are not output columns: their new value is 0
-        for (int k = lane; k < h.nkp; k += 32) {
-            const T q = qk[k];
-            if (q != (T)0 && ((__ldg(sv.kmask + (k >> 5)) >> (k & 31)) & 1u) == 0u) sq_add(pos, (double)q * (double)q);
-        }
-        const Sq128 rowsq = sq_group_sum(pos, 32);
-        if (fits) for (int k = written + lane; k < h.no; k += 32) { a.out.cols[base + k] = -1; a.out.vals[base + k] = (T)0; }
-        if (lane == 0) {
-            a.out.row_ptr[row] = fits ? base : 0;
-            a.out.row_len[row] = fits ? written : 0;
-            t_sq2 += rowsq.hi;
-            t_sq1 += rowsq.lo >> 32;
-            t_sq0 += rowsq.lo & 0xffffffffull;
-            t_kept += (unsigned long long)s_nk[r];
-            t_nnz += (unsigned long long)written;
-            t_max_len = max(t_max_len, written);
-            t_max_kept = max(t_max_kept, h.nkp);
-        }
-    }
-    pdl_launch_dependents();
-
-    // ---- publish the CTA's totals (lane 0 of every warp holds its rows' sums)
+// What the rows of a thread add up to: the squares per lane (exact, so the grouping is free), the counts in lane 0.
+// Reduced over the warp and published once per CTA.
+struct RowTotals {
+    Sq128 sq;
+    unsigned long long nnz, kept;
+    int max_kept, max_len;
+};
+__device__ __forceinline__ void publish_totals(WalkState* st, const RowTotals& t) {      // CTA-wide
     __shared__ unsigned long long s_tot[5];
     __shared__ int s_max[2];
     if (threadIdx.x < 5) s_tot[threadIdx.x] = 0ull;
     if (threadIdx.x < 2) s_max[threadIdx.x] = 0;
     __syncthreads();
-    if (lane == 0) {
-        if (t_sq0) atomicAdd(&s_tot[0], t_sq0);
-        if (t_sq1) atomicAdd(&s_tot[1], t_sq1);
-        if (t_sq2) atomicAdd(&s_tot[2], t_sq2);
-        if (t_nnz) atomicAdd(&s_tot[3], t_nnz);
-        if (t_kept) atomicAdd(&s_tot[4], t_kept);
-        if (t_max_kept) atomicMax(&s_max[0], t_max_kept);
-        if (t_max_len) atomicMax(&s_max[1], t_max_len);
+    const Sq128 wsq = sq_group_sum(t.sq, 32);
+    if (lane_id() == 0) {
+        const unsigned long long sq0 = wsq.lo & 0xffffffffull, sq1 = wsq.lo >> 32, sq2 = wsq.hi;
+        if (sq0) atomicAdd(&s_tot[0], sq0);
+        if (sq1) atomicAdd(&s_tot[1], sq1);
+        if (sq2) atomicAdd(&s_tot[2], sq2);
+        if (t.nnz) atomicAdd(&s_tot[3], t.nnz);
+        if (t.kept) atomicAdd(&s_tot[4], t.kept);
+        if (t.max_kept) atomicMax(&s_max[0], t.max_kept);
+        if (t.max_len) atomicMax(&s_max[1], t.max_len);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -274,8 +173,701 @@ __global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArg
         if (s_max[0]) atomicMax(&st->max_kept, s_max[0]);
         if (s_max[1]) atomicMax(&st->max_row_len, s_max[1]);
     }
-    if (win_mode) win_flush(wacc, stage, a.cand, a.cand_cap, st);
-    else if (a.hist) hist_window_flush<T>(a.hist, win);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Numeric pass over blocks b0, b0 + bstride, ... of one row by one warp.  q_s (shared memory) holds the row's previous
+// values in structure order with everything at or below the cut replaced by 0.  Output p of block b is owned by lane
+// p & 31; round j of the block holds the j-th product of every output with more than j products - counts descend
+// inside a block, so the active lanes are a prefix and the round's entries sit at off + lane.  The loads of kNumR
+// rounds are issued before the first of them is consumed (the sums themselves stay strictly in order).
+// SRC: where the structure is read from - kStaged: shared memory (one round ahead is enough); kGlobalRO: global memory,
+// written by an earlier kernel (read-only path); kGlobal: global memory, written by this CTA just now.
+// ---------------------------------------------------------------------------------------------
+constexpr int kNumR = 8;
+constexpr int kStaged = 0, kGlobalRO = 1, kGlobal = 2;
+
+template <typename T, int SRC>
+__device__ __forceinline__ void numeric_blocks(const PropArgs<T>& a, const unsigned char* blk, int no, int nprod, int dpos,
+                                               const T* q_s, long long slot, SelCtx<T>& sel, RowTotals& tot, int b0, int bstride) {
+    constexpr bool NC = SRC == kGlobalRO;
+    const StructLayout L = struct_layout<T>(no, nprod);
+    const int32_t* bptr = reinterpret_cast<const int32_t*>(blk + L.bptr);
+    const uint16_t* cnt = reinterpret_cast<const uint16_t*>(blk + L.cnt);
+    const uint16_t* ck = reinterpret_cast<const uint16_t*>(blk + L.ck);
+    const T* cw = reinterpret_cast<const T*>(blk + L.cw);
+    const int lane = lane_id();
+    const int nb = (no + 31) >> 5;
+    T* ov = a.out.vals + slot;
+    Sq128 sq = tot.sq;
+    int nz = 0;
+    int c_n = 0, off_n = 0;
+    if (b0 < nb) {
+        const int p = (b0 << 5) + lane;
+        if (p < no) c_n = NC ? (int)__ldg(cnt + p) : (int)cnt[p];
+        off_n = NC ? __ldg(bptr + b0) : bptr[b0];
+    }
+    for (int b = b0; b < nb; b += bstride) {
+        const int p = (b << 5) + lane;
+        const bool act = p < no;
+        const int c = c_n;
+        int off = off_n;
+        if (b + bstride < nb) {         // next block's counts while this one is summed
+            const int pn = ((b + bstride) << 5) + lane;
+            c_n = 0;
+            if (pn < no) c_n = NC ? (int)__ldg(cnt + pn) : (int)cnt[pn];
+            off_n = NC ? __ldg(bptr + b + bstride) : bptr[b + bstride];
+        }
+        const int maxc = __shfl_sync(kFull, c, 0);
+        T acc = (T)0;
+        if (SRC != kStaged) {
+            // global memory: the loads of kNumR rounds go out before the first of them is consumed
+            for (int j0 = 0; j0 < maxc; j0 += kNumR) {
+                unsigned kk[kNumR];
+                T ww[kNumR];
+#pragma unroll
+                for (int r = 0; r < kNumR; ++r) {
+                    const bool on = j0 + r < c;
+                    kk[r] = 0u; ww[r] = (T)0;
+                    if (on) { kk[r] = NC ? __ldg(ck + off + lane) : ck[off + lane]; ww[r] = NC ? __ldg(cw + off + lane) : cw[off + lane]; }
+                    off += __popc(__ballot_sync(kFull, on));
+                }
+#pragma unroll
+                for (int r = 0; r < kNumR; ++r)
+                    if (j0 + r < c) acc = add_rn(acc, mul_rn(q_s[kk[r]], ww[r]));
+            }
+        } else {
+            // shared memory: one round ahead is enough
+            unsigned k_n = 0u;
+            T w_n = (T)0;
+            if (c > 0) { k_n = ck[off + lane]; w_n = cw[off + lane]; }
+            for (int j = 0; j < maxc; ++j) {
+                const bool on = j < c;
+                const unsigned k = k_n;
+                const T w = w_n;
+                off += __popc(__ballot_sync(kFull, on));
+                if (j + 1 < c) { k_n = ck[off + lane]; w_n = cw[off + lane]; }
+                if (on) acc = add_rn(acc, mul_rn(q_s[k], w));
+            }
+        }
+        T v = (T)0;
+        if (act) {
+            v = mul_rn(a.scale, acc);
+            if (p == dpos) v = add_rn(v, a.restart);
+            const T d = sub_rn(q_s[p], v);
+            sq_add(sq, (double)d * (double)d);
+            ov[p] = v;
+        }
+        const bool nzv = act && v != (T)0;
+        sel.add(nzv, v);
+        nz += __popc(__ballot_sync(kFull, nzv));
+    }
+    tot.sq = sq;
+    if (lane == 0) tot.nnz += (unsigned long long)nz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The fast kernel: one warp per row, rows dealt round robin over a grid that fills the GPU once.  Every warp runs a
+// two-stage pipeline of its own: while row i is validated and summed out of shared memory, the bulk copies (TMA) of row
+// i + stride - its previous values and the hot part of its pool block - are in flight, completing on the stage's
+// mbarrier.  A row that does not fit a stage is read straight from global memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFastStages = 2;
+struct FastShape {
+    int no_max;         // outputs per row a stage holds
+    int hot_max;        // bytes of the pool block's hot part a stage holds (multiple of 16)
+    size_t stage;       // bytes per stage
+    size_t smem;        // dynamic shared memory per CTA
+};
+template <typename T>
+__host__ __device__ inline FastShape fast_shape(int no_max, int hot_max) {
+    FastShape f;
+    f.no_max = no_max;
+    f.hot_max = (hot_max + 15) & ~15;
+    f.stage = align16((size_t)no_max * sizeof(T)) + (size_t)f.hot_max;
+    f.smem = (size_t)kFastWarps * kFastStages * f.stage + align16((size_t)kHistWin * 4);
+    return f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArgs<T> a, FastShape fs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned int s_wn;
+    __shared__ __align__(8) unsigned long long s_bar[kFastWarps][kFastStages];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    unsigned char* my = smem_raw + (size_t)warp * kFastStages * fs.stage;
+    unsigned int* win = reinterpret_cast<unsigned int*>(smem_raw + (size_t)kFastWarps * kFastStages * fs.stage);
+    const size_t vals_bytes = align16((size_t)fs.no_max * sizeof(T));
+    for (int i = threadIdx.x; i < kHistWin; i += blockDim.x) win[i] = 0u;
+    if (threadIdx.x == 0) s_wn = 0u;
+    if (lane == 0) {
+        for (int g = 0; g < kFastStages; ++g) mbar_init(&s_bar[warp][g], 1u);
+        fence_mbar_init();
+    }
+    pdl_wait();
+    WalkState* st = a.st;
+    if (st->done) return;
+    __syncthreads();
+    const bool cut_on = __ldcg(&st->cut_on) != 0;
+    const T cut = (T)__ldcg(&st->cut);
+    const unsigned gen = __ldcg(&st->pool_gen);
+    const int step = __ldcg(&st->step);
+    SelCtx<T> sel = make_sel<T>(a, win, &s_wn);
+    RowTotals tot = {{0ull, 0ull}, 0ull, 0ull, 0, 0};
+    int n_fast = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->unordered_rows = 1;
+
+    // what the pipeline keeps of a header; kind 0: no usable structure (slow list), 1: staged through shared memory,
+    // 2: read from global memory
+    struct Hdr { long long off, slot; int no, nprod, dpos, nk, hot, kind; };
+    auto load_hdr = [&](int row) -> Hdr {
+        const RowStruct r = a.rs[row];
+        Hdr h;
+        h.off = r.off; h.slot = r.slot; h.no = r.no; h.nprod = r.nprod; h.dpos = r.dpos; h.nk = r.nk; h.hot = r.hot_bytes;
+        h.kind = 0;
+        if (cut_on && r.gen == gen && gen != 0u && r.step == step - 1 && r.no > 0)
+            h.kind = (r.no <= fs.no_max && r.hot_bytes <= fs.hot_max) ? 1 : 2;
+        return h;
+    };
+    auto issue = [&](const Hdr& h, int g) {               // lane 0: the stage is free and behind a proxy fence
+        const unsigned vb = (unsigned)align16((size_t)h.no * sizeof(T));
+        const unsigned hb = (unsigned)h.hot;
+        unsigned char* dst = my + (size_t)g * fs.stage;
+        mbar_expect_tx(&s_bar[warp][g], vb + hb);
+        bulk_g2s(dst, a.in.vals + h.slot, vb, &s_bar[warp][g]);
+        bulk_g2s(dst + vals_bytes, a.pool + h.off, hb, &s_bar[warp][g]);
+    };
+
+    const int stride = gridDim.x * kFastWarps;
+    const int row0 = blockIdx.x * kFastWarps + warp;
+    // three headers in registers: the row at hand, the next (its copies are in flight), the one after (copies go out
+    // when the row at hand has released its stage)
+    Hdr h0, h1, h2;
+    h0.kind = 0; h1.kind = 0; h2.kind = 0;
+    if (row0 < a.n_rows) h0 = load_hdr(row0);
+    if (row0 + stride < a.n_rows) h1 = load_hdr(row0 + stride);
+    if (row0 + 2 * stride < a.n_rows) h2 = load_hdr(row0 + 2 * stride);
+    if (h0.kind == 1 && lane == 0) issue(h0, 0);
+    if (h1.kind == 1 && lane == 0) issue(h1, 1);
+    unsigned phase = 0u;        // bit g: parity the next wait on stage g expects
+    int g = 0;
+    for (int row = row0; row < a.n_rows; row += stride) {
+        const Hdr h = h0;
+        const int kind = h.kind;
+        unsigned char* stg = my + (size_t)g * fs.stage;
+        T* q_s = reinterpret_cast<T*>(stg);
+        bool ok = kind != 0;
+        int nkept = 0;
+        if (kind == 1) {
+            mbar_wait(&s_bar[warp][g], (phase >> g) & 1u);
+            phase ^= 1u << g;
+        }
+        if (ok) {
+            const StructLayout L = struct_layout<T>(h.no, h.nprod);
+            const uint32_t* kbits = kind == 1 ? reinterpret_cast<const uint32_t*>(stg + vals_bytes + L.kbits)
+                                              : reinterpret_cast<const uint32_t*>(a.pool + h.off + L.kbits);
+            const T* rv = kind == 1 ? q_s : a.in.vals + h.slot;
+            bool bad = false;
+            if (kind == 2 && h.no > fs.no_max) bad = true;          // no room for the previous values: rebuild (the symbolic kernel defers it)
+            else
+            for (int b = 0; b < h.no; b += 128) {
+                T v[4];
+                unsigned kb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int p = b + u * 32 + lane;
+                    v[u] = (T)0; kb[u] = 0u;
+                    if (p < h.no) v[u] = rv[p];
+                    if (b + u * 32 < h.no) kb[u] = kbits[(b >> 5) + u];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int p = b + u * 32 + lane;
+                    const bool kept = v[u] > cut;
+                    if (kept && ((kb[u] >> lane) & 1u) == 0u) bad = true;
+                    if (p < h.no) q_s[p] = kept ? v[u] : (T)0;
+                    nkept += __popc(__ballot_sync(kFull, kept));
+                }
+            }
+            ok = !__any_sync(kFull, bad);
+        }
+        if (ok) {
+            __syncwarp();
+            if (kind == 1) numeric_blocks<T, kStaged>(a, stg + vals_bytes, h.no, h.nprod, h.dpos, q_s, h.slot, sel, tot, 0, 1);
+            else numeric_blocks<T, kGlobalRO>(a, a.pool + h.off, h.no, h.nprod, h.dpos, q_s, h.slot, sel, tot, 0, 1);
+            if (lane == 0) {
+                a.out.row_ptr[row] = h.slot;
+                a.out.row_len[row] = h.no;
+                a.rs[row].step = step;
+                tot.kept += (unsigned long long)nkept;
+                tot.max_len = max(tot.max_len, h.no);
+                tot.max_kept = max(tot.max_kept, h.nk);
+            }
+            ++n_fast;
+        } else if (lane == 0) {
+            a.slow_list[atomicAdd(&st->slow_count, 1u)] = row;
+        }
+        // the stage is released: copies of the row after next, header of the one after that
+        fence_proxy_async();
+        __syncwarp();
+        h0 = h1;
+        h1 = h2;
+        if (row + 2 * stride >= a.n_rows) h1.kind = 0;
+        if (h1.kind == 1 && lane == 0) issue(h1, g);
+        h2.kind = 0;
+        if (row + 3 * stride < a.n_rows) h2 = load_hdr(row + 3 * stride);
+        g ^= 1;
+    }
+    pdl_launch_dependents();
+    if (lane == 0 && n_fast) atomicAdd(&st->fast_rows, (unsigned)n_fast);
+    publish_totals(st, tot);
+    sel.flush(st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The symbolic kernel: one CTA per row of the slow list (every row on the first structure step).  Everything is
+// parallel over the row's PRODUCTS (operand k of K+ times entry of P row k), which are dealt to the threads in stream
+// order (k ascending, P-row order):
+//   P1  K+ = the row's entries above alpha x cut (q = the value where it is above the cut, else 0), sorted by column
+//   P2  hash table of the output set (K+ itself, the restart column, every column a product reaches) with the number
+//       of products per output; slot and operand of every product are remembered
+//   P3  outputs sorted by count, descending (counting sort); block offsets
+//   P4  the products into one staging list per output, IN STREAM ORDER: the operands are taken in windows of 32; the
+//       products of a window set their operand's bit in the output's window mask, a product's place is the output's
+//       fill level before the window plus the number of lower bits in the mask
+//   P5  pool block: the lists of a block's 32 outputs interleaved round by round; fixed slot; header
+//   P6  numeric pass on the fresh structure (the CTA's warps share the row's blocks)
+// Nothing depends on the order in which threads run, except the order of the outputs inside a count class (arbitrary;
+// it only decides where a value is stored, never its bits).
+// ---------------------------------------------------------------------------------------------
+struct SymShape {
+    int H;              // hash slots (power of two, >= 2 * no_max + 64)
+    int no_max;         // outputs a row may have
+    int km;             // operand columns (|K+|) a row may have
+    int threads;        // CTA size for short lists (the first build uses threads_build)
+    int threads_build;
+    int tmp_smem;       // products staged in shared memory; longer rows stage in global memory
+    int tmp_cap;        // products per global staging region (one per CTA)
+    size_t smem;        // dynamic shared memory per CTA (window included)
+};
+__host__ __device__ inline size_t sym_smem_bytes(int H, int no_max, int km, int tmp_smem, size_t s) {
+    const size_t nbm = (size_t)(no_max + 31) / 32;
+    return align16((size_t)H * 4) * 3 + align16((size_t)H * 2) +     // hkey, hcnt, wmask, hpos
+           align16((size_t)km * 4) * 2 + align16((size_t)km * s) + align16((size_t)(km + 2) * 4) * 2 +   // kcol, kps, kval, kpre, bins
+           align16((size_t)km * 2) * 2 +                              // kslot, kpos
+           align16((size_t)no_max * 2) * 3 +                          // olist, oslot, cnt_s
+           align16((size_t)no_max * 4) +                              // cptr
+           align16((size_t)no_max * s) +                              // q_s
+           align16((nbm + 1) * 4) * 2 +                               // bptr_s, kb_s
+           align16((size_t)tmp_smem * 2) * 3 + align16((size_t)tmp_smem * s) +   // pslot, pk, tck, tcw
+           align16((size_t)kHistWin * 4);                             // select window
+}
+__host__ __device__ inline size_t sym_tmp_bytes(int tmp_cap, size_t s) {        // one CTA's global staging region
+    return align16((size_t)tmp_cap * 2) * 3 + align16((size_t)tmp_cap * s);
+}
+
+__device__ __forceinline__ uint32_t sym_hash(int32_t j, int mask) { return (((uint32_t)j * 0x9E3779B1u) >> 7) & (uint32_t)mask; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape sh) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned int s_wn;
+    __shared__ int s_nk, s_nkt, s_nout, s_nprod;
+    __shared__ unsigned long long s_slot_base, s_slot_left, s_pool_base, s_pool_left, s_slot_rel, s_poff;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int lane = lane_id();
+    const int warp = tid >> 5;
+    const int W = nth >> 5;
+    const int H = sh.H, HM = sh.H - 1, NOMAX = sh.no_max, KM = sh.km;
+    const size_t s = sizeof(T);
+    unsigned char* p = smem_raw;
+    int32_t* hkey = reinterpret_cast<int32_t*>(p);      p += align16((size_t)H * 4);
+    int32_t* hcnt = reinterpret_cast<int32_t*>(p);      p += align16((size_t)H * 4);
+    uint32_t* wmask = reinterpret_cast<uint32_t*>(p);   p += align16((size_t)H * 4);
+    uint16_t* hpos = reinterpret_cast<uint16_t*>(p);    p += align16((size_t)H * 2);
+    int32_t* kcol = reinterpret_cast<int32_t*>(p);      p += align16((size_t)KM * 4);
+    int32_t* kps = reinterpret_cast<int32_t*>(p);       p += align16((size_t)KM * 4);
+    T* kval = reinterpret_cast<T*>(p);                  p += align16((size_t)KM * s);
+    int32_t* kpre = reinterpret_cast<int32_t*>(p);      p += align16((size_t)(KM + 2) * 4);
+    int32_t* bins = reinterpret_cast<int32_t*>(p);      p += align16((size_t)(KM + 2) * 4);
+    uint16_t* kslot = reinterpret_cast<uint16_t*>(p);   p += align16((size_t)KM * 2);
+    uint16_t* kpos = reinterpret_cast<uint16_t*>(p);    p += align16((size_t)KM * 2);
+    uint16_t* olist = reinterpret_cast<uint16_t*>(p);   p += align16((size_t)NOMAX * 2);
+    uint16_t* oslot = reinterpret_cast<uint16_t*>(p);   p += align16((size_t)NOMAX * 2);
+    uint16_t* cnt_s = reinterpret_cast<uint16_t*>(p);   p += align16((size_t)NOMAX * 2);
+    int32_t* cptr = reinterpret_cast<int32_t*>(p);      p += align16((size_t)NOMAX * 4);
+    T* q_s = reinterpret_cast<T*>(p);                   p += align16((size_t)NOMAX * s);
+    const size_t nbm = (size_t)(NOMAX + 31) / 32;
+    int32_t* bptr_s = reinterpret_cast<int32_t*>(p);    p += align16((nbm + 1) * 4);
+    uint32_t* kb_s = reinterpret_cast<uint32_t*>(p);    p += align16((nbm + 1) * 4);
+    uint16_t* pslot_s = reinterpret_cast<uint16_t*>(p); p += align16((size_t)sh.tmp_smem * 2);
+    uint16_t* pk_s = reinterpret_cast<uint16_t*>(p);    p += align16((size_t)sh.tmp_smem * 2);
+    uint16_t* tck_s = reinterpret_cast<uint16_t*>(p);   p += align16((size_t)sh.tmp_smem * 2);
+    T* tcw_s = reinterpret_cast<T*>(p);                 p += align16((size_t)sh.tmp_smem * s);
+    unsigned int* win = reinterpret_cast<unsigned int*>(p);
+    // the unsorted K+ is parked in cptr / q_s (KM <= NOMAX) until it has been sorted into kcol / kval
+    int32_t* kcol_u = cptr;
+    T* kval_u = q_s;
+
+    for (int i = tid; i < kHistWin; i += nth) win[i] = 0u;
+    for (int i = tid; i < H; i += nth) { hkey[i] = -1; hcnt[i] = 0; wmask[i] = 0u; }
+    if (tid == 0) { s_wn = 0u; s_slot_left = 0ull; s_pool_left = 0ull; s_slot_base = 0ull; s_pool_base = 0ull; }
+    pdl_wait();
+    WalkState* st = a.st;
+    if (st->done) return;
+    __syncthreads();
+    const bool cut_on = __ldcg(&st->cut_on) != 0;
+    const T cut = (T)__ldcg(&st->cut);
+    const T cut_lo = (T)((double)a.alpha * (double)cut);
+    const unsigned gen = __ldcg(&st->pool_gen);
+    const int step = __ldcg(&st->step);
+    const int n_list = a.row_list_count ? (int)__ldcg(a.row_list_count) : a.n_rows;
+    SelCtx<T> sel = make_sel<T>(a, win, &s_wn);
+    RowTotals tot = {{0ull, 0ull}, 0ull, 0ull, 0, 0};
+    int n_built = 0;
+    long long hot_delta = 0;
+    if (blockIdx.x == 0 && tid == 0) {
+        st->unordered_rows = 1;
+        if (!cut_on && n_list > 0) st->order_hazard = 1;      // structures only exist behind a cut (never for positive data)
+    }
+    // few rows (settled walk): exact reservations; many (first build): a CTA reserves for several rows at a time
+    const bool chunked = n_list > 2 * (int)gridDim.x;
+    unsigned char* gtmp = a.sym_tmp + (size_t)blockIdx.x * sym_tmp_bytes(sh.tmp_cap, s);
+    uint16_t* pslot_g = reinterpret_cast<uint16_t*>(gtmp);              gtmp += align16((size_t)sh.tmp_cap * 2);
+    uint16_t* pk_g = reinterpret_cast<uint16_t*>(gtmp);                 gtmp += align16((size_t)sh.tmp_cap * 2);
+    uint16_t* tck_g = reinterpret_cast<uint16_t*>(gtmp);                gtmp += align16((size_t)sh.tmp_cap * 2);
+    T* tcw_g = reinterpret_cast<T*>(gtmp);
+    const int32_t* __restrict__ pcols = a.p_cols;
+    const T* __restrict__ pvals = a.p_vals;
+
+    auto find = [&](int32_t j) -> int {             // slot of a column that is in the table
+        int sl = (int)sym_hash(j, HM);
+        CRWR_GUARD_DECL(g);
+        while (hkey[sl] != j) { sl = (sl + 1) & HM; CRWR_GUARD(st, g, H, 7, break); }
+        return sl;
+    };
+    auto insert = [&](int32_t j) -> int {
+        int sl = (int)sym_hash(j, HM);
+        for (;;) {
+            const int32_t k = hkey[sl];
+            if (k == j) return sl;
+            if (k == -1) {
+                const int32_t o = atomicCAS(&hkey[sl], -1, j);
+                if (o == -1) {
+                    const int idx = atomicAdd(&s_nout, 1);
+                    if (idx < NOMAX) olist[idx] = (uint16_t)sl;
+                    return sl;
+                }
+                if (o == j) return sl;
+            }
+            sl = (sl + 1) & HM;
+        }
+    };
+    // entries of a reserved chunk of the slot region that no row received: zero (a whole-array select pass covers them)
+    auto zero_slots = [&](unsigned long long base, unsigned long long left) {
+        for (unsigned long long i = tid; i < left && base + i < (unsigned long long)a.slot_cap; i += nth) {
+            a.in.vals[a.fixed_base + (long long)(base + i)] = (T)0;
+            a.out.vals[a.fixed_base + (long long)(base + i)] = (T)0;
+        }
+    };
+
+    if (cut_on)
+    for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+        const int row = a.row_list_count ? __ldg(a.row_order + li) : li;
+        const int32_t dcol = a.row_begin + row;
+        const RowStruct old = a.rs[row];
+        if (tid == 0) { s_nk = 0; s_nkt = 0; s_nout = 0; }
+        __syncthreads();
+        // ---- P1: K+ (unordered), then sorted by column (rank by counting)
+        const long long ptr = a.in.row_ptr[row];
+        const int len = a.in.row_len[row];
+        for (int b = 0; b < len; b += nth) {
+            const int e = b + tid;
+            T v = (T)0;
+            int32_t c = 0;
+            if (e < len) { v = __ldg(a.in.vals + ptr + e); c = __ldg(a.in.cols + ptr + e); }
+            const bool keep = v > cut_lo;
+            const bool kt = v > cut;
+            const unsigned m = __ballot_sync(kFull, keep);
+            const unsigned mt = __ballot_sync(kFull, kt);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_nk, __popc(m));
+            if (lane == 0 && mt) atomicAdd(&s_nkt, __popc(mt));
+            base = __shfl_sync(kFull, base, 0);
+            const int pos = base + __popc(m & lanemask_lt());
+            if (keep && pos < KM) { kcol_u[pos] = c; kval_u[pos] = kt ? v : (T)0; }
+        }
+        // the row's old fixed slot (if any) is abandoned: no stale value may be left for a whole-array select pass.
+        // The copy in this step's output buffer now; the one in the input buffer (the row's operand) once it is no
+        // longer needed - below, or by the large-row kernel when the row is deferred to it.
+        const bool had_slot = old.gen == gen && old.no > 0;
+        if (had_slot) {
+            for (int i = tid; i < old.no; i += nth) a.out.vals[old.slot + i] = (T)0;
+            if (tid == 0) { a.rs[row].gen = 0u; hot_delta -= (long long)old.hot_bytes; }
+        }
+        __syncthreads();
+        const int nk = s_nk, nkt = s_nkt;
+        bool defer = nk > KM;
+        int no = 0, nprod = 0;
+        if (!defer) {
+            for (int i = tid; i < nk; i += nth) {
+                const int32_t c = kcol_u[i];
+                int r = 0;
+                for (int j = 0; j < nk; ++j) r += (kcol_u[j] < c) ? 1 : 0;
+                kcol[r] = c;
+                kval[r] = kval_u[i];
+                const int ps = __ldg(a.p_indptr + c);
+                kps[r] = ps;
+                kpre[r + 1] = __ldg(a.p_indptr + c + 1) - ps;         // lengths first, prefix sums next
+            }
+            for (int i = tid; i <= nk; i += nth) bins[i] = 0;
+            __syncthreads();
+            if (warp == 0) {
+                int run = 0;
+                for (int b = 0; b < nk; b += 32) {
+                    const int i = b + lane;
+                    const int l = i < nk ? kpre[i + 1] : 0;
+                    int incl = l;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    if (i < nk) kpre[i + 1] = run + incl;
+                    run += __shfl_sync(kFull, incl, 31);
+                }
+                if (lane == 0) { kpre[0] = 0; s_nprod = run; }
+            }
+            __syncthreads();
+            nprod = s_nprod;
+            if (nprod > sh.tmp_smem && nprod > sh.tmp_cap) defer = true;
+        }
+        uint16_t* pslot = nprod <= sh.tmp_smem ? pslot_s : pslot_g;
+        uint16_t* pk = nprod <= sh.tmp_smem ? pk_s : pk_g;
+        uint16_t* tck = nprod <= sh.tmp_smem ? tck_s : tck_g;
+        T* tcw = nprod <= sh.tmp_smem ? tcw_s : tcw_g;
+        if (!defer) {
+            // ---- P2: the output set and the products per output
+            for (int i = tid; i < nk; i += nth) kslot[i] = (uint16_t)insert(kcol[i]);
+            if (tid == 0) insert(dcol);
+            for (int i = tid; i < nprod; i += nth) {
+                int lo = 0, hi = nk - 1;                    // operand of product i: kpre[k] <= i < kpre[k + 1]
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (kpre[mid + 1] <= i) lo = mid + 1; else hi = mid;
+                }
+                int sl = 0;
+                if (s_nout <= NOMAX) {
+                    const int32_t j = __ldg(pcols + kps[lo] + (i - kpre[lo]));
+                    CRWR_CHECK(st, j >= 0, 5);
+                    sl = insert(j);
+                    atomicAdd(&hcnt[sl], 1);
+                }
+                pslot[i] = (uint16_t)sl;
+                pk[i] = (uint16_t)lo;
+            }
+            __syncthreads();
+            no = s_nout;
+            if (no > NOMAX) defer = true;
+        }
+        if (!defer) {
+            // ---- P3: counting sort by count, descending; block offsets
+            for (int o = tid; o < no; o += nth) atomicAdd(&bins[hcnt[olist[o]]], 1);
+            __syncthreads();
+            if (warp == 0) {
+                int run = 0;
+                for (int hi = nk; hi >= 0; hi -= 32) {
+                    const int c = hi - lane;
+                    const int v = c >= 0 ? bins[c] : 0;
+                    int incl = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= o) incl += u;
+                    }
+                    if (c >= 0) bins[c] = run + incl - v;
+                    run += __shfl_sync(kFull, incl, 31);
+                }
+            }
+            __syncthreads();
+            for (int o = tid; o < no; o += nth) {
+                const int sl = olist[o];
+                const int c = hcnt[sl];
+                const int pos = atomicAdd(&bins[c], 1);
+                oslot[pos] = (uint16_t)sl;
+                cnt_s[pos] = (uint16_t)c;
+                hpos[sl] = (uint16_t)pos;
+                hcnt[sl] = 0;                   // from here on: the output's fill level
+            }
+            __syncthreads();
+            const int nb = (no + 31) >> 5;
+            for (int b = warp; b < nb; b += W) {
+                const int pp = (b << 5) + lane;
+                const int c = pp < no ? (int)cnt_s[pp] : 0;
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                if (pp < no) { cptr[pp] = incl - c; q_s[pp] = (T)0; }     // relative to the block's offset
+                if (lane == 31) { bptr_s[b] = incl; kb_s[b] = 0u; }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int run = 0;
+                for (int b0 = 0; b0 <= nb; b0 += 32) {
+                    const int b = b0 + lane;
+                    const int v = b < nb ? bptr_s[b] : 0;
+                    int incl = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= o) incl += u;
+                    }
+                    if (b <= nb) bptr_s[b] = run + incl - v;
+                    run += __shfl_sync(kFull, incl, 31);
+                }
+            }
+            __syncthreads();
+            CRWR_CHECK(st, bptr_s[nb] == nprod, 8);
+        }
+        unsigned long long slot_rel = 0, poff = 0;
+        const StructLayout L = struct_layout<T>(no, nprod);
+        const unsigned long long no4 = (unsigned long long)((no + 3) & ~3);     // slots start on 16-byte boundaries (bulk copies)
+        if (!defer) {
+            // ---- reservations: fixed slot in both iterate buffers, pool block (thread 0; chunked while many rows are built)
+            if (no4 > s_slot_left) zero_slots(s_slot_base, s_slot_left);
+            __syncthreads();
+            if (tid == 0) {
+                if (no4 > s_slot_left) {
+                    const unsigned long long sz = (chunked && (unsigned long long)a.slot_chunk > no4) ? (unsigned long long)a.slot_chunk : no4;
+                    s_slot_base = atomicAdd(&st->slot_cursor, sz);
+                    s_slot_left = sz;
+                }
+                s_slot_rel = s_slot_base; s_slot_base += no4; s_slot_left -= no4;
+                if ((unsigned long long)L.bytes > s_pool_left) {
+                    const unsigned long long sz = (chunked && (unsigned long long)a.pool_chunk > (unsigned long long)L.bytes) ? (unsigned long long)a.pool_chunk : (unsigned long long)L.bytes;
+                    s_pool_base = atomicAdd(&st->pool_cursor, sz);
+                    s_pool_left = sz;
+                }
+                s_poff = s_pool_base; s_pool_base += (unsigned long long)L.bytes; s_pool_left -= (unsigned long long)L.bytes;
+            }
+            __syncthreads();
+            slot_rel = s_slot_rel; poff = s_poff;
+            if (slot_rel + no4 > (unsigned long long)a.slot_cap || poff + L.bytes > a.pool_cap) {
+                // slot region or pool exhausted: the row goes without a structure (large-row kernel), this step and - as
+                // the cursors only grow - every later one; struct_full tells the host a larger workspace would be faster
+                if (tid == 0) st->struct_full = 1;
+                zero_slots(slot_rel, no4);          // the slot entries it did get stay empty
+                defer = true;
+            }
+        }
+        if (defer) {
+            // too large for the tables: the large-row kernel computes the row, it keeps no structure
+            if (no > NOMAX) { for (int i = tid; i < H; i += nth) { hkey[i] = -1; hcnt[i] = 0; } }
+            else for (int i = tid; i < no; i += nth) { const int sl = olist[i]; hkey[sl] = -1; hcnt[sl] = 0; }
+            if (tid == 0) { a.fb_rows[atomicAdd(&st->fb_count, 1u)] = row; tot.max_kept = max(tot.max_kept, nk); }
+            __syncthreads();
+            continue;
+        }
+        const long long slot = a.fixed_base + (long long)slot_rel;
+        unsigned char* blk = a.pool + poff;
+        const int nb = (no + 31) >> 5;
+        if (tid < (int)no4 - no) { a.in.vals[slot + no + tid] = (T)0; a.out.vals[slot + no + tid] = (T)0; }
+        if (had_slot) for (int i = tid; i < old.no; i += nth) a.in.vals[old.slot + i] = (T)0;
+        // positions of the operands, K+ membership bits, previous values in structure order
+        for (int i = tid; i < nk; i += nth) {
+            const int pos = hpos[kslot[i]];
+            kpos[i] = (uint16_t)pos;
+            q_s[pos] = kval[i];
+            atomicOr(&kb_s[pos >> 5], 1u << (pos & 31));
+        }
+        const int dpos = hpos[find(dcol)];
+        __syncthreads();
+        // ---- P4: the products into the staging lists, in stream order, one window of 32 operands at a time
+        for (int w0 = 0; w0 < nk; w0 += 32) {
+            const int i_lo = kpre[w0], i_hi = kpre[min(w0 + 32, nk)];
+            for (int i = i_lo + tid; i < i_hi; i += nth) atomicOr(&wmask[pslot[i]], 1u << ((int)pk[i] - w0));
+            __syncthreads();
+            for (int i = i_lo + tid; i < i_hi; i += nth) {
+                const int sl = pslot[i], k = pk[i];
+                const unsigned bit = 1u << (k - w0);
+                const int pos = hpos[sl];
+                const int at = bptr_s[pos >> 5] + cptr[pos] + hcnt[sl] + __popc(wmask[sl] & (bit - 1u));
+                CRWR_CHECK(st, at >= 0 && at < nprod, 9);
+                tck[at] = kpos[k];
+                tcw[at] = __ldg(pvals + kps[k] + (i - kpre[k]));
+            }
+            __syncthreads();
+            for (int i = i_lo + tid; i < i_hi; i += nth) {
+                const int sl = pslot[i];
+                const unsigned m = wmask[sl];
+                const unsigned bit = 1u << ((int)pk[i] - w0);
+                // the output's first product of the window updates its fill level (a later one may already see the mask cleared)
+                if (m != 0u && (m & (bit - 1u)) == 0u) { hcnt[sl] += __popc(m); wmask[sl] = 0u; }
+            }
+            __syncthreads();
+        }
+        // ---- P5: the pool block; the staging lists interleaved round by round; the slot's columns (written once)
+        {
+            int32_t* ocols_w = reinterpret_cast<int32_t*>(blk + L.ocols);
+            int32_t* bptr_w = reinterpret_cast<int32_t*>(blk + L.bptr);
+            uint32_t* kbits_w = reinterpret_cast<uint32_t*>(blk + L.kbits);
+            uint16_t* cnt_w = reinterpret_cast<uint16_t*>(blk + L.cnt);
+            uint16_t* ck_w = reinterpret_cast<uint16_t*>(blk + L.ck);
+            T* cw_w = reinterpret_cast<T*>(blk + L.cw);
+            for (int i = tid; i <= nb; i += nth) bptr_w[i] = bptr_s[i];
+            for (int i = tid; i < nb; i += nth) kbits_w[i] = kb_s[i];
+            for (int b = warp; b < nb; b += W) {
+                const int pp = (b << 5) + lane;
+                int c = 0, src = 0;
+                if (pp < no) {
+                    const int sl = oslot[pp];
+                    const int32_t col = hkey[sl];
+                    c = (int)cnt_s[pp];
+                    src = bptr_s[b] + cptr[pp];
+                    ocols_w[pp] = col;
+                    cnt_w[pp] = (uint16_t)c;
+                    a.in.cols[slot + pp] = col;
+                    a.out.cols[slot + pp] = col;
+                }
+                int off = bptr_s[b];
+                const int maxc = __shfl_sync(kFull, c, 0);
+                for (int j = 0; j < maxc; ++j) {
+                    const bool on = j < c;
+                    if (on) { ck_w[off + lane] = tck[src + j]; cw_w[off + lane] = tcw[src + j]; }
+                    off += __popc(__ballot_sync(kFull, on));
+                }
+            }
+        }
+        __syncthreads();
+        // the table is released; header
+        for (int i = tid; i < no; i += nth) { const int sl = oslot[i]; hkey[sl] = -1; hcnt[sl] = 0; }
+        if (tid == 0) {
+            RowStruct hd;
+            hd.off = (long long)poff; hd.slot = slot; hd.no = no; hd.nprod = nprod; hd.nk = nk; hd.dpos = dpos;
+            hd.gen = gen; hd.step = step; hd.hot_bytes = (int32_t)L.hot_bytes; hd.pad = 0;
+            a.rs[row] = hd;
+            a.out.row_ptr[row] = slot;
+            a.out.row_len[row] = no;
+            tot.kept += (unsigned long long)nkt;
+            tot.max_len = max(tot.max_len, no);
+            tot.max_kept = max(tot.max_kept, nk);
+            hot_delta += (long long)L.hot_bytes;
+        }
+        // ---- P6: numeric pass on the fresh structure
+        numeric_blocks<T, kGlobal>(a, blk, no, nprod, dpos, q_s, slot, sel, tot, warp, W);
+        ++n_built;
+        __syncthreads();
+    }
+    zero_slots(s_slot_base, s_slot_left);
+    pdl_launch_dependents();
+    if (tid == 0 && n_built) atomicAdd(&st->built_rows, (unsigned)n_built);
+    if (tid == 0 && hot_delta) atomicAdd(&st->hot_sum, (unsigned long long)hot_delta);
+    publish_totals(st, tot);
+    sel.flush(st);
 }
 
 }  // namespace crwr

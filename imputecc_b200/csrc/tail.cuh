@@ -21,6 +21,7 @@ namespace crwr {
 struct TailArgs {
     FinishArgs fin;
     const void* vals;               // value array of this step's product (full select on a window miss)
+    long long fixed_base;           // first entry of its fixed-slot region
     unsigned long long* cand;       // candidate block [count, successor, keys...]
     unsigned long long cand_cap;
 };
@@ -51,7 +52,7 @@ __device__ __noinline__ void full_select_one_cta(const TailArgs& a, unsigned cha
     unsigned long long* H = a.fin.hist + kXExtras;
     unsigned int* sh = reinterpret_cast<unsigned int*>(scratch);
     const T* vals = reinterpret_cast<const T*>(a.vals);
-    const long long nvals = (long long)st->cursor;
+    const ValRanges nvals = val_ranges(st, a.fixed_base);
     const int t = threadIdx.x;
     if (!hist0_valid) {
         for (int i = t; i < kSelectLevels * kSelectBins; i += blockDim.x) H[i] = 0ull;

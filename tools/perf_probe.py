@@ -38,9 +38,6 @@ for rep in range(args.reps):
     ph = (_lib.C.c_double * 3)()
     lib.crwr_profile_phases(w.handle, ph)
     print("rep %d: %d steps, wall %.3f ms, propagate total %.3f ms over %d launches | phases: prop+dense %.3f hist1 %.3f gather+finish %.3f" % (rep, st.steps_done, wall * 1e3, tot.value, nl.value, ph[0], ph[1], ph[2]))
-pn = (_lib.C.c_uint64 * 8)()
-lib.crwr_phase_ns(w.handle, pn, w._stream())
-print("phase us (last walk): propagate %.1f | barrier %.1f | scan %.1f | barrier %.1f | l1+gather %.1f | barrier %.1f | finish %.1f | barrier %.1f" % tuple(x / 1e3 for x in pn))
 shape = (_lib.C.c_int64 * 8)()
 lib.crwr_get_shape(w.handle, shape)
 print("shape H %d limit %d kmax %d scap %d warps %d per_warp %d grid %d sms %d" % tuple(shape))
@@ -48,6 +45,7 @@ gs = (_lib.C.c_int64 * 8)()
 lib.crwr_get_group_shape(w.handle, gs)
 print("group shape H %d limit %d kmax %d ov %d G %d warps %d per_row %d grid %d" % tuple(gs))
 for t in w.trace():
-    print("step %2d in %8d new %9d maxrow %5d maxkept %5d fallback %5d cut %.3e delta %.4f" %
-          (t["step"], t["nnz_in"], t["nnz_new"], t["max_row_len"], t["max_kept"], t["fallback_rows"], t["cut"], t["delta"]))
+    print("step %2d in %8d new %9d maxrow %5d maxkept %5d fallback %5d fast %6d cut %.3e delta %.4f" %
+          (t["step"], t["nnz_in"], t["nnz_new"], t["max_row_len"], t["max_kept"], t["fallback_rows"], t["fast_rows"], t["cut"], t["delta"]))
+print("retries", w.retries, "regrows", w.regrows)
 w.close()
