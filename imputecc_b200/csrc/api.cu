@@ -979,7 +979,7 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     if (const char* k = getenv("CRWR_ROW_ORDER")) h->use_order = atoi(k) != 0;
     h->structs_on = env_int("CRWR_STRUCT", 1) != 0;
     h->timeline = env_int("CRWR_TIMELINE", 0) != 0;
-    h->build_step = env_int("CRWR_BUILD_STEP", 2);
+    h->build_step = env_int("CRWR_BUILD_STEP", 3);
     if (h->build_step < 2) h->build_step = 2;       // structures only exist behind a cut
     h->win_step = env_int("CRWR_WIN_STEP", 6);
     if (h->win_step > 0 && h->win_step < 2) h->win_step = 2;

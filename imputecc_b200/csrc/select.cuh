@@ -199,7 +199,8 @@ constexpr size_t kFinishScratchBytes = sizeof(unsigned long long) * (kCandSmem +
 
 // free_bits: low key bits in which the candidates may differ (-1: everything below the 24-bit prefix of the gather pass)
 template <typename T>
-__device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned char* scratch, int free_bits = -1) {
+__device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned char* scratch, int free_bits = -1,
+                                                 bool preloaded = false, bool hist_clean = false) {
     typedef KeyOf<T> KO;
     typedef typename KO::type K;
     unsigned long long* sk = reinterpret_cast<unsigned long long*>(scratch);
@@ -220,7 +221,7 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
     WalkState& s_state = *s_state_p;
     WalkState* const gst = a.st;
     const int t = threadIdx.x;
-    {
+    if (!preloaded) {
         const unsigned* src = reinterpret_cast<const unsigned*>(gst);
         unsigned* dst = reinterpret_cast<unsigned*>(&s_state);
         for (int i = t; i < (int)(sizeof(WalkState) / 4); i += blockDim.x) dst[i] = __ldcg(src + i);
@@ -257,11 +258,15 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
             __syncthreads();
             cand = a.merged;
         }
+        // a candidate set that fits shared memory is brought there once (the radix passes would read it three times)
+        if (!s_ovf && c <= (unsigned long long)kCandSmem) {
+            for (unsigned int i = t; i < c; i += blockDim.x) sk[i] = cand[i];
+            __syncthreads();
+            if (free_bits >= 0 && c > 512ull) cand = sk;
+        }
         if (s_ovf) {
             // handled below (sticky error)
         } else if (c <= (unsigned long long)(free_bits >= 0 ? 512 : kCandSmem)) {
-            for (unsigned int i = t; i < c; i += blockDim.x) sk[i] = cand[i];
-            __syncthreads();
             for (unsigned int i = t; i < c; i += blockDim.x) {
                 const unsigned long long me = sk[i];
                 unsigned long long rank = 0;
@@ -419,7 +424,14 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
         unsigned* dst = reinterpret_cast<unsigned*>(gst);
         for (int i = t; i < (int)(sizeof(WalkState) / 4); i += blockDim.x) dst[i] = src[i];
     }
-    for (int i = t; i < kSelectLevels * kSelectBins + kXExtras; i += blockDim.x) a.hist[i] = 0ull;
+    if (!hist_clean) for (int i = t; i < kSelectLevels * kSelectBins + kXExtras; i += blockDim.x) a.hist[i] = 0ull;
+}
+
+// Where finish_step_body keeps the walk state inside its scratch (for a caller that loads it beforehand).
+__device__ __forceinline__ WalkState* finish_state_ptr(unsigned char* scratch) {
+    unsigned long long* sk = reinterpret_cast<unsigned long long*>(scratch);
+    unsigned int* sh_hist = reinterpret_cast<unsigned int*>(sk + kCandSmem + 4 + 32 + 4);
+    return reinterpret_cast<WalkState*>(reinterpret_cast<int*>(sh_hist + 256) + 4);
 }
 
 #undef s_xk

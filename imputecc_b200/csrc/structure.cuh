@@ -267,6 +267,76 @@ __device__ __forceinline__ void numeric_blocks(const PropArgs<T>& a, const unsig
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same numeric pass for a row staged in shared memory, U blocks of 32 outputs at a time: the sums of one output are
+// a chain of dependent additions, so the warp's only instruction-level parallelism is across blocks.  Blocks are sorted
+// by count, so the U blocks of an iteration have similar round counts (the first has the most).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int U>
+__device__ __forceinline__ void numeric_staged(const PropArgs<T>& a, const unsigned char* blk, int no, int nprod, int dpos,
+                                               const T* q_s, long long slot, SelCtx<T>& sel, RowTotals& tot) {
+    const StructLayout L = struct_layout<T>(no, nprod);
+    const int32_t* bptr = reinterpret_cast<const int32_t*>(blk + L.bptr);
+    const uint16_t* cnt = reinterpret_cast<const uint16_t*>(blk + L.cnt);
+    const uint16_t* ck = reinterpret_cast<const uint16_t*>(blk + L.ck) + lane_id();
+    const T* cw = reinterpret_cast<const T*>(blk + L.cw) + lane_id();
+    const int lane = lane_id();
+    const int nb = (no + 31) >> 5;
+    T* ov = a.out.vals + slot;
+    Sq128 sq = tot.sq;
+    int nz = 0;
+    for (int b = 0; b < nb; b += U) {
+        int c[U], off[U];
+        T acc[U];
+        unsigned kn[U];
+        T wn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = ((b + u) << 5) + lane;
+            c[u] = 0; off[u] = 0; acc[u] = (T)0; kn[u] = 0u; wn[u] = (T)0;
+            if (b + u < nb) {
+                if (p < no) c[u] = (int)cnt[p];
+                off[u] = bptr[b + u];
+            }
+        }
+        const int maxc = __shfl_sync(kFull, c[0], 0);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (c[u] > 0) { kn[u] = ck[off[u]]; wn[u] = cw[off[u]]; }
+        for (int j = 0; j < maxc; ++j) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool on = j < c[u];
+                const unsigned k = kn[u];
+                const T w = wn[u];
+                off[u] += __popc(__ballot_sync(kFull, on));
+                if (j + 1 < c[u]) { kn[u] = ck[off[u]]; wn[u] = cw[off[u]]; }
+                if (on) acc[u] = add_rn(acc[u], mul_rn(q_s[k], w));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (b + u < nb) {
+                const int p = ((b + u) << 5) + lane;
+                const bool act = p < no;
+                T v = (T)0;
+                if (act) {
+                    v = mul_rn(a.scale, acc[u]);
+                    if (p == dpos) v = add_rn(v, a.restart);
+                    const T d = sub_rn(q_s[p], v);
+                    sq_add(sq, (double)d * (double)d);
+                    ov[p] = v;
+                }
+                const bool nzv = act && v != (T)0;
+                sel.add(nzv, v);
+                nz += __popc(__ballot_sync(kFull, nzv));
+            }
+        }
+    }
+    tot.sq = sq;
+    if (lane == 0) tot.nnz += (unsigned long long)nz;
+}
+
+// ---------------------------------------------------------------------------------------------
 // The fast kernel: one warp per row, rows dealt round robin over a grid that fills the GPU once.  Every warp runs a
 // two-stage pipeline of its own: while row i is validated and summed out of shared memory, the bulk copies (TMA) of row
 // i + stride - its previous values and the hot part of its pool block - are in flight, completing on the stage's
@@ -394,7 +464,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArg
         }
         if (ok) {
             __syncwarp();
-            if (kind == 1) numeric_blocks<T, kStaged>(a, stg + vals_bytes, h.no, h.nprod, h.dpos, q_s, h.slot, sel, tot, 0, 1);
+            if (kind == 1) numeric_staged<T, 2>(a, stg + vals_bytes, h.no, h.nprod, h.dpos, q_s, h.slot, sel, tot);
             else numeric_blocks<T, kGlobalRO>(a, a.pool + h.off, h.no, h.nprod, h.dpos, q_s, h.slot, sel, tot, 0, 1);
             if (lane == 0) {
                 a.out.row_ptr[row] = h.slot;
@@ -437,7 +507,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArg
 //       products of a window set their operand's bit in the output's window mask, a product's place is the output's
 //       fill level before the window plus the number of lower bits in the mask
 //   P5  pool block: the lists of a block's 32 outputs interleaved round by round; fixed slot; header
-//   P6  numeric pass on the fresh structure (the CTA's warps share the row's blocks)
+//   P6  numeric pass, fused into P5: the lane that copies an output's list also sums it
 // Nothing depends on the order in which threads run, except the order of the outputs inside a count class (arbitrary;
 // it only decides where a value is stored, never its bits).
 // ---------------------------------------------------------------------------------------------
@@ -835,11 +905,30 @@ __global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape s
                 }
                 int off = bptr_s[b];
                 const int maxc = __shfl_sync(kFull, c, 0);
+                T acc = (T)0;
                 for (int j = 0; j < maxc; ++j) {
                     const bool on = j < c;
-                    if (on) { ck_w[off + lane] = tck[src + j]; cw_w[off + lane] = tcw[src + j]; }
+                    if (on) {
+                        const unsigned k = tck[src + j];
+                        const T w = tcw[src + j];
+                        ck_w[off + lane] = (uint16_t)k;
+                        cw_w[off + lane] = w;
+                        acc = add_rn(acc, mul_rn(q_s[k], w));        // P6: the numeric pass, on the way
+                    }
                     off += __popc(__ballot_sync(kFull, on));
                 }
+                T v = (T)0;
+                if (pp < no) {
+                    v = mul_rn(a.scale, acc);
+                    if (pp == dpos) v = add_rn(v, a.restart);
+                    const T d = sub_rn(q_s[pp], v);
+                    sq_add(tot.sq, (double)d * (double)d);
+                    a.out.vals[slot + pp] = v;
+                }
+                const bool nzv = pp < no && v != (T)0;
+                sel.add(nzv, v);
+                const int nzc = __popc(__ballot_sync(kFull, nzv));
+                if (lane == 0) tot.nnz += (unsigned long long)nzc;
             }
         }
         __syncthreads();
@@ -857,8 +946,6 @@ __global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape s
             tot.max_kept = max(tot.max_kept, nk);
             hot_delta += (long long)L.hot_bytes;
         }
-        // ---- P6: numeric pass on the fresh structure
-        numeric_blocks<T, kGlobal>(a, blk, no, nprod, dpos, q_s, slot, sel, tot, warp, W);
         ++n_built;
         __syncthreads();
     }

@@ -82,11 +82,19 @@ __global__ void __launch_bounds__(1024) tail_kernel(TailArgs a) {
     __shared__ int s_hit, s_free;
     pdl_wait();
     pdl_launch_dependents();
-    WalkState* st = a.fin.st;
+    WalkState* gst = a.fin.st;
+    // the walk state in one coalesced read (thread 0 would otherwise make a dozen dependent L2 round trips)
+    WalkState* st = finish_state_ptr(scratch);
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(gst);
+        unsigned* dst = reinterpret_cast<unsigned*>(st);
+        for (int i = threadIdx.x; i < (int)(sizeof(WalkState) / 4); i += blockDim.x) dst[i] = __ldcg(src + i);
+    }
+    __syncthreads();
     if (st->done) return;
+    const bool win = st->win_on != 0;
     if (threadIdx.x == 0) {
         const unsigned long long n = st->nnz_exact;
-        const bool win = st->win_on != 0;
         int hit = 0, free_bits = -1;
         if (win && n > 0) {
             virtual_index<T>(st, n);
@@ -102,14 +110,21 @@ __global__ void __launch_bounds__(1024) tail_kernel(TailArgs a) {
                 if (free_bits < 1) free_bits = 1;
             }
         }
-        if (!hit) st->win_miss_steps += 1;
         s_hit = hit;
         s_free = free_bits;
     }
     __syncthreads();
-    if (!s_hit) full_select_one_cta<T>(a, scratch, st->win_on == 0);
+    if (s_hit) {
+        // the window held: the histograms were not touched this step and stay clear
+        finish_step_body<T>(a.fin, scratch, s_free, true, true);
+        return;
+    }
+    // a miss: the complete select on the state in global memory, then the ordinary finish (which loads it again)
+    if (threadIdx.x == 0) gst->win_miss_steps += 1;
     __syncthreads();
-    finish_step_body<T>(a.fin, scratch, s_hit ? s_free : -1);
+    full_select_one_cta<T>(a, scratch, !win);
+    __syncthreads();
+    finish_step_body<T>(a.fin, scratch, -1);
 }
 
 }  // namespace crwr
