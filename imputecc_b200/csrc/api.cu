@@ -230,9 +230,13 @@ struct crwr_handle_s {
     unsigned long long* peer_block = nullptr;   // this rank's symmetric block
     unsigned long long peer_epoch_base = 0;
     bool hist0_fused = false;                   // sharded step: level-0 histogram already filled by propagate
-    bool structs_on = true;                     // CRWR_STRUCT=0: no cached row structures (row-group kernel every step)
+    int struct_mode = 1;                        // CRWR_STRUCT: 0 no cached row structures (row-group kernel every step), 1 when
+                                                // the rows are long enough to pay for them (default), 2 always
+    long long struct_min_row = 256;             // ... mean stored entries per row from which they pay (CRWR_STRUCT_MIN_ROW)
+    long long mean_row = 0;                     // mean stored entries per row at the last poll
+    bool structs_active = false;                // this walk's decision, taken when the first structure step is queued
     int win_step = 6;                           // first walk step whose cut comes from the window select (CRWR_WIN_STEP; 0: never)
-    float alpha = 0.3f;                         // K+ = entries above alpha x cut (CRWR_STRUCT_ALPHA)
+    float alpha = 0.5f;                         // K+ = entries above alpha x cut (CRWR_STRUCT_ALPHA)
     float win_scale = 2.5f, win_min = 0.004f, win_max = 0.15f, win_rel_max = 0.10f;
     bool dense_always = false;                  // a step deferred rows while no large-row kernel was queued: always queue it
     bool fb_seen = false;                       // this walk has deferred rows before (polled)
@@ -240,6 +244,9 @@ struct crwr_handle_s {
     int sym_grid = 0;
     int fast_no = 0, fast_grid = 0;             // fast kernel: outputs per row it holds (0: kernel unusable), persistent grid
     FastShape fshape = {0, 0, 0, 0};
+    size_t big_smem = 0;                        // big-row kernel (structure.cuh): shared memory, persistent grid
+    int big_grid = 0;
+    bool big_seen = false;                      // this walk has long rows (polled): the big-row kernel is queued
     long long avg_hot = 0;                      // mean pool bytes per row of this walk's structures (polled; 0: unknown)
     bool fast_retune = false;                   // avg_hot moved: the next crwr_set_row_hints sizes the fast kernel again
     int build_step = 2;                         // first walk step that runs the symbolic kernel (CRWR_BUILD_STEP, >= 2)
@@ -369,6 +376,7 @@ int configure_struct_shape(crwr_handle_s* h, long long max_row_len, long long ma
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, symbolic_kernel<T>, sh.threads_build, sh.smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
+    if (per_sm == 1) { sh.threads = 512; sh.threads_build = 512; }      // long rows: shared memory admits one CTA per SM, so it gets more threads
     long long grid = (long long)per_sm * h->sm_count;
     const long long max_ctas = rows < kSymMaxCtas ? rows : kSymMaxCtas;
     if (grid > max_ctas) grid = max_ctas;
@@ -380,7 +388,7 @@ int configure_struct_shape(crwr_handle_s* h, long long max_row_len, long long ma
     // most for the longest row the symbolic kernel stages, and shrunk until two CTAs fit an SM.
     {
         long long prods = sh.tmp_smem;
-        size_t hot = struct_layout<T>(sh.no_max, (int)prods).hot_bytes;
+        size_t hot = struct_layout<T>(sh.no_max, (int)prods, 1).hot_bytes;
         if (h->avg_hot > 0) {
             size_t want = (size_t)(2.5 * (double)h->avg_hot);
             if (want < 2048) want = 2048;
@@ -401,6 +409,16 @@ int configure_struct_shape(crwr_handle_s* h, long long max_row_len, long long ma
             h->fast_no = sh.no_max;
             h->fshape = f;
             h->fast_grid = per_sm * h->sm_count;
+            // the big-row kernel: previous values and sums of one row per CTA
+            const size_t bs = big_smem_bytes<T>(sh.no_max);
+            e = raise_smem_attr(propagate_fast_big_kernel<T>, bs);
+            if (e != cudaSuccess) return (int)e;
+            int big_per_sm = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&big_per_sm, propagate_fast_big_kernel<T>, kBigGroups * 32, bs);
+            if (e != cudaSuccess) return (int)e;
+            if (big_per_sm < 1) big_per_sm = 1;
+            h->big_smem = bs;
+            h->big_grid = big_per_sm * h->sm_count;
             if (h->timeline)
                 fprintf(stderr, "shapes: fast no_max %d hot_max %d stage %zu smem %zu CTAs/SM %d (mean hot %lld) | symbolic H %d no_max %d km %d tmp_smem %d smem %zu grid %d\n",
                         f.no_max, f.hot_max, f.stage, f.smem, per_sm, h->avg_hot, sh.H, sh.no_max, sh.km, sh.tmp_smem, sh.smem, h->sym_grid);
@@ -564,6 +582,8 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     a.fixed_base = L.fixed_base;
     a.slot_cap = L.slot_cap;
     a.sym_tmp = h->at<unsigned char>(L.sym_tmp);
+    a.small_no = h->fshape.no_max;
+    a.small_hot = h->fshape.hot_max;
 
     {
         // while many rows are built a warp reserves slot entries / pool bytes for about four rows at a time
@@ -627,7 +647,9 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, bool win_step, cu
     }
     const int rows = a.n_rows;
     const bool pdl = use_pdl(h);
-    const bool structs = h->structs_on && h->prop_kind == 1 && step >= h->build_step && h->fast_no > 0;
+    if (step == h->build_step)
+        h->structs_active = h->struct_mode == 2 || (h->struct_mode == 1 && h->mean_row >= h->struct_min_row);
+    const bool structs = h->structs_active && h->prop_kind == 1 && step >= h->build_step && h->fast_no > 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
         if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
@@ -636,6 +658,13 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, bool win_step, cu
     tl_mark(h, st, "step start");
     if (structs) {
         a.row_order = nullptr;
+        if (step > h->build_step && h->big_seen) {
+            launch_k(pdl, propagate_fast_big_kernel<T>, rows < h->big_grid ? rows : h->big_grid, kBigGroups * 32, h->big_smem, st, a,
+                     h->fshape, h->sym.no_max);
+            ++g_launches;
+            if (cudaGetLastError() != cudaSuccess) return -1;
+            tl_mark(h, st, "fast (long rows)");
+        }
         if (step > h->build_step) {
             int grid = (rows + kFastWarps - 1) / kFastWarps;
             if (grid > h->fast_grid) grid = h->fast_grid;
@@ -977,15 +1006,17 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     if (const char* k = getenv("CRWR_PROP")) h->prop_kind = strcmp(k, "warp") == 0 ? 0 : 1;
     if (const char* k = getenv("CRWR_PDL")) h->pdl_forced = atoi(k) != 0 ? 1 : 0;
     if (const char* k = getenv("CRWR_ROW_ORDER")) h->use_order = atoi(k) != 0;
-    h->structs_on = env_int("CRWR_STRUCT", 1) != 0;
+    h->struct_mode = env_int("CRWR_STRUCT", 1);
+    if (h->struct_mode < 0 || h->struct_mode > 2) h->struct_mode = 1;
+    h->struct_min_row = env_int("CRWR_STRUCT_MIN_ROW", 256);
     h->timeline = env_int("CRWR_TIMELINE", 0) != 0;
     h->build_step = env_int("CRWR_BUILD_STEP", 3);
     if (h->build_step < 2) h->build_step = 2;       // structures only exist behind a cut
     h->win_step = env_int("CRWR_WIN_STEP", 6);
     if (h->win_step > 0 && h->win_step < 2) h->win_step = 2;
     if (h->prop_kind != 1) h->win_step = 0;         // the warp-per-row kernel only knows the histogram select
-    h->alpha = (float)env_double("CRWR_STRUCT_ALPHA", 0.3);
-    if (!(h->alpha > 0.f && h->alpha <= 1.f)) h->alpha = 0.3f;
+    h->alpha = (float)env_double("CRWR_STRUCT_ALPHA", 0.5);
+    if (!(h->alpha > 0.f && h->alpha <= 1.f)) h->alpha = 0.5f;
     h->win_scale = (float)env_double("CRWR_WIN_SCALE", 2.5);
     h->win_min = (float)env_double("CRWR_WIN_MIN", 0.004);
     h->win_max = (float)env_double("CRWR_WIN_MAX", 0.15);
@@ -1125,6 +1156,9 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     h->perc = perc;
     h->steps_enqueued = 0;
     h->avg_hot = 0;
+    h->mean_row = 0;
+    h->structs_active = false;
+    h->big_seen = false;
     h->fb_seen = false;
     h->dense_launched = true;
     h->order_valid = false;
@@ -1418,6 +1452,12 @@ int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
     // the host-side step counter follows the device: steps enqueued past the stop were skipped
     if (s.done) h->steps_enqueued = s.step;
     if (s.last_fallback_rows > 0) h->fb_seen = true;
+    if (s.big_rows > 0) h->big_seen = true;
+    {
+        // (a sharded walk's count is the sum over all ranks, its rows are the markers)
+        const long long rows = h->cfg.n_shards > 1 ? h->cfg.n_markers : h->cfg.row_end - h->cfg.row_begin;
+        h->mean_row = (long long)(s.last_nnz_new / (unsigned long long)(rows > 0 ? rows : 1));
+    }
     if (s.hot_sum > 0) {
         const long long rows = h->cfg.row_end - h->cfg.row_begin;
         const long long avg = (long long)(s.hot_sum / (unsigned long long)(rows > 0 ? rows : 1));

@@ -120,11 +120,14 @@ struct WalkState {
     // cached row structures (structure.cuh): rows whose kept set lies inside the cached superset take the fast kernel
     unsigned long long pool_cursor;    // bytes of the structure pool in use
     unsigned long long slot_cursor;    // entries of the fixed-slot region (both iterate buffers) in use
+    unsigned long long last_nnz_new;   // stored entries of the last finished step's product (all ranks)
     unsigned long long hot_sum;        // bytes of the hot parts of all current structures (mod 2^64; the host sizes the fast kernel's stages)
     unsigned int pool_gen;             // generation of this walk's structures (0 in a header = no structure)
     int32_t struct_full;               // sticky: slot region or pool exhausted, later rows went without a structure
     unsigned int slow_count;           // rows the fast kernel handed to the row-group kernel this step
-    unsigned int fast_rows;            // rows the fast kernel computed this step
+    unsigned int fast_rows;            // rows the fast kernels computed this step
+    unsigned int big_rows;             // long rows among them / built this step (the host then queues the big-row kernel)
+    unsigned int pad8;
     unsigned int built_rows;           // structures built this step
     int32_t fb_unhandled;              // sticky: rows were deferred in a step that launched no large-row kernel (host retries)
     // window select (tail.cuh): the epilogues collect the values in [win_lo, win_hi) as percentile candidates
@@ -208,7 +211,7 @@ struct RowStruct {
     uint32_t gen;           // walk generation the block belongs to; 0 = no structure
     int32_t step;           // last walk step that wrote the row in structure order into its slot
     int32_t hot_bytes;      // bytes of the block's hot part (what the fast kernel stages in shared memory)
-    int32_t pad;
+    int32_t groups;         // groups the outputs are dealt to (1, or kBigGroups for a long row)
 };
 
 template <typename T>

@@ -53,6 +53,7 @@ struct PropArgs {
     int32_t slot_chunk;         // symbolic kernel: entries / bytes a warp reserves at a time while many rows are built
     int32_t pool_chunk;
     unsigned char* sym_tmp;     // symbolic kernel: per-CTA staging regions (rows too long for shared-memory staging)
+    int32_t small_no, small_hot;   // symbolic kernel: what a stage of the fast kernel holds (outputs, bytes); longer rows get groups
     int32_t win_mode;           // classify values against the select window when the walk state has one
     unsigned long long* cand;   // candidate block [count, successor, keys...] of the window select
     unsigned long long cand_cap;

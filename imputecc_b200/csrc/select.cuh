@@ -380,6 +380,7 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
             st->order_hazard = 1;
         st->unordered_rows = 0;
         st->last_delta = delta;
+        st->last_nnz_new = nnz_new;
         st->cut_on = cut_applied;
         if (cut_applied) st->cut = cut;
         st->parity ^= 1;

@@ -7,50 +7,60 @@
 // entries above alpha x cut, alpha < 1) and cached in a pool:
 //     O             the output columns K+ reaches, plus K+ itself and the restart column, sorted by the number
 //                   of products that feed them (descending) - this is also the row's STORAGE ORDER from now on
-//     per output    its products (position of the operand in O, P value) in ascending operand column = exactly
-//                   scipy's summation order; the lists of the 32 outputs of a block are interleaved round by
-//                   round (round j holds the j-th product of every output that has one), so a warp reads them
-//                   with fully coalesced loads and no padding
+//     streams       the outputs are dealt to G groups (G = 1, or 8 for a long row) and inside a group to the 32 lanes
+//                   of a warp, chunk of 32 by chunk, in alternating direction (so every lane gets a similar number
+//                   of products although the counts are heavily skewed); a lane's products - operand position in O,
+//                   P value - follow each other output by output, inside an output in ascending operand column =
+//                   exactly scipy's summation order, the last product of an output flagged.  Round j of a group's
+//                   stream holds the j-th product of every lane that has one: contiguous, read once, front to back.
 // and the row gets a FIXED slot of |O| entries in both iterate buffers.  A later step may use the structure
 // whenever its kept set is INSIDE K+ (one bit per output): members of K+ at or below the cut take q = 0, their
 // products are exact zeros and adding them changes no bit; outputs reached only through them come out 0 and
-// count as absent, like csr_matmat drops them.  The numeric pass (numeric_row) is then output-stationary: one
-// lane per output adds that output's products in order (separate multiply and add, as everywhere) - no hash
-// table, no atomics, no sorting, no allocation, and the previous value of the same output (for ||Q - Q~||) sits
-// at the same position of the input row.
+// count as absent, like csr_matmat drops them.  The numeric pass (numeric_stream) is then output-stationary: a
+// lane adds the products of its outputs in order (separate multiply and add, as everywhere) - no hash table, no
+// atomics, no sorting, no allocation, and the previous value of the same output (for ||Q - Q~||) sits at the same
+// position of the input row.
 //
-// fast_kernel       rows with a current structure: validate (kept set inside K+), numeric pass; others -> slow list
-// symbolic_kernel   rows of the slow list (all rows on the first structure step): build the structure, numeric pass
+// fast_kernel       short rows with a current structure, a warp each: the row's previous values and streams are
+//                   brought into shared memory by bulk copies (TMA), two rows in flight per warp
+// fast_big_kernel   long rows with a current structure, a CTA each (a warp per group), streams read from global memory
+// symbolic_kernel   rows whose kept set left K+ (all rows on the first structure step): build the structure,
+//                   numeric pass on the way
 // Rows that exceed the symbolic kernel's tables go to the large-row kernel (fb_rows) and keep no structure.
 #pragma once
 #include "propagate.cuh"
 
 namespace crwr {
 
-constexpr int kFastWarps = 4;               // warps per CTA of the fast kernel
-constexpr int kSymMaxCtas = 148 * 8;         // CTAs of one symbolic_kernel launch (each owns a global staging region)
+constexpr int kFastWarps = 4;               // warps per CTA of the fast kernels
+constexpr int kBigGroups = 8;               // groups of a long row (= warps of the CTA that replays it)
+constexpr int kSymMaxCtas = 148 * 8;        // CTAs of one symbolic_kernel launch (each owns a global staging region)
+constexpr unsigned kLastFlag = 0x8000u;     // stream entry: last product of its output
 
-// Pool block of one row, nb = ceil(no / 32).  The part the numeric pass reads comes first, 16-byte aligned and a
-// multiple of 16 bytes long, so that one bulk copy (TMA) brings it into shared memory:
-//   [bptr (nb+1) x i32][kbits nb x u32][cnt no x u16](pad 4)[ck nprod x u16](pad 16)[cw nprod x T](pad 16) | [ocols no x i32]
-struct StructLayout { size_t ocols, bptr, kbits, cnt, ck, cw, hot_bytes, bytes; };
+// Pool block of one row, nb = ceil(no / 32), G groups.  The part the numeric pass reads comes first, 16-byte aligned
+// and a multiple of 16 bytes long, so that one bulk copy (TMA) brings it into shared memory:
+//   [lload G*32 x u16][gptr (G+1) x i32][kbits nb x u32][ck nprod x u16](pad 16)[cw nprod x T](pad 16) | [ocols no x i32]
+struct StructLayout { uint32_t lload, gptr, kbits, ck, cw, hot_bytes, ocols, bytes; };
 template <typename T>
-__host__ __device__ inline StructLayout struct_layout(int no, int nprod) {
-    const size_t nb = (size_t)((no + 31) >> 5);
+__host__ __device__ inline StructLayout struct_layout(int no, int nprod, int G) {
+    const uint32_t nb = (uint32_t)((no + 31) >> 5);
     StructLayout L;
-    size_t o = 0;
-    L.bptr = o;  o += 4 * (nb + 1);
-    L.kbits = o; o += 4 * nb;
-    L.cnt = o;   o += 2 * (size_t)no;
-    o = (o + 3) & ~(size_t)3;
-    L.ck = o;    o += 2 * (size_t)nprod;
-    o = (o + 15) & ~(size_t)15;
-    L.cw = o;    o += sizeof(T) * (size_t)nprod;
-    o = (o + 15) & ~(size_t)15;
+    uint32_t o = 0;
+    L.lload = o; o += 2u * 32u * (uint32_t)G;
+    L.gptr = o;  o += 4u * (uint32_t)(G + 1);
+    L.kbits = o; o += 4u * nb;
+    L.ck = o;    o += 2u * (uint32_t)nprod;
+    o = (o + 15u) & ~15u;
+    L.cw = o;    o += (uint32_t)sizeof(T) * (uint32_t)nprod;
+    o = (o + 15u) & ~15u;
     L.hot_bytes = o;
-    L.ocols = o; o += 4 * (size_t)no;
-    L.bytes = (o + 15) & ~(size_t)15;
+    L.ocols = o; o += 4u * (uint32_t)no;
+    L.bytes = (o + 15u) & ~15u;
     return L;
+}
+// Position of the output that lane `lane` of group g owns in the group's ii-th chunk (the direction alternates).
+__device__ __forceinline__ int lane_pos(int ii, int g, int G, int lane) {
+    return ((ii * G + g) << 5) + ((ii & 1) ? 31 - lane : lane);
 }
 
 // ---- bulk asynchronous copies global -> shared (TMA, cp.async.bulk) completing on an mbarrier
@@ -176,83 +186,68 @@ __device__ __forceinline__ void publish_totals(WalkState* st, const RowTotals& t
 }
 
 // ---------------------------------------------------------------------------------------------
-// Numeric pass over blocks b0, b0 + bstride, ... of one row by one warp.  q_s (shared memory) holds the row's previous
-// values in structure order with everything at or below the cut replaced by 0.  Output p of block b is owned by lane
-// p & 31; round j of the block holds the j-th product of every output with more than j products - counts descend
-// inside a block, so the active lanes are a prefix and the round's entries sit at off + lane.  The loads of kNumR
-// rounds are issued before the first of them is consumed (the sums themselves stay strictly in order).
-// SRC: where the structure is read from - kStaged: shared memory (one round ahead is enough); kGlobalRO: global memory,
-// written by an earlier kernel (read-only path); kGlobal: global memory, written by this CTA just now.
+// Numeric pass of one group of a row by one warp.  q_s (shared memory) holds the row's previous values in structure
+// order with everything at or below the cut replaced by 0; res_s (shared memory) receives the sums.  The lane walks
+// its share of the group's stream: round j of the stream holds the j-th product of every lane with more than j
+// products, in lane order.  The loads of RN rounds are issued before the first of them is consumed (the sums
+// themselves stay strictly in order).  Then the epilogue over the group's chunks: scale, restart, norm, select, store.
+// SRC: kStaged - the structure lies in shared memory; kGlobalRO - in global memory, written by an earlier kernel.
 // ---------------------------------------------------------------------------------------------
-constexpr int kNumR = 8;
-constexpr int kStaged = 0, kGlobalRO = 1, kGlobal = 2;
+constexpr int kStaged = 0, kGlobalRO = 1;
 
 template <typename T, int SRC>
-__device__ __forceinline__ void numeric_blocks(const PropArgs<T>& a, const unsigned char* blk, int no, int nprod, int dpos,
-                                               const T* q_s, long long slot, SelCtx<T>& sel, RowTotals& tot, int b0, int bstride) {
+__device__ __forceinline__ void numeric_stream(const PropArgs<T>& a, const unsigned char* blk, int no, int nprod, int G, int g,
+                                               int dpos, const T* q_s, T* res_s, long long slot, SelCtx<T>& sel, RowTotals& tot) {
     constexpr bool NC = SRC == kGlobalRO;
-    const StructLayout L = struct_layout<T>(no, nprod);
-    const int32_t* bptr = reinterpret_cast<const int32_t*>(blk + L.bptr);
-    const uint16_t* cnt = reinterpret_cast<const uint16_t*>(blk + L.cnt);
+    constexpr int RN = SRC == kStaged ? 4 : 8;
+    const StructLayout L = struct_layout<T>(no, nprod, G);
+    const uint16_t* lload = reinterpret_cast<const uint16_t*>(blk + L.lload);
+    const int32_t* gptr = reinterpret_cast<const int32_t*>(blk + L.gptr);
     const uint16_t* ck = reinterpret_cast<const uint16_t*>(blk + L.ck);
     const T* cw = reinterpret_cast<const T*>(blk + L.cw);
     const int lane = lane_id();
     const int nb = (no + 31) >> 5;
+    const int load = NC ? (int)__ldg(lload + g * 32 + lane) : (int)lload[g * 32 + lane];
+    int off = NC ? __ldg(gptr + g) : gptr[g];
+    const int rounds = __reduce_max_sync(kFull, load);
+    // The sums are parked by (chunk of the group, owning lane): res_s[ii * 32 * G + g * 32 + lane] - the group's ii-th
+    // chunk occupies the 32 entries of chunk ii * G + g.  Outputs without a product keep 0.
+    for (int c = g; c < nb; c += G) res_s[(c << 5) + lane] = (T)0;
+    __syncwarp();
+    T acc = (T)0;
+    T* res_cur = res_s + (g << 5) + lane;
+    const int res_step = G << 5;
+    for (int j0 = 0; j0 < rounds; j0 += RN) {
+        unsigned e[RN];
+        T w[RN];
+#pragma unroll
+        for (int r = 0; r < RN; ++r) {
+            const bool on = j0 + r < load;
+            const unsigned m = __ballot_sync(kFull, on);
+            const int idx = off + __popc(m & lanemask_lt());
+            e[r] = 0u; w[r] = (T)0;
+            if (on) { e[r] = NC ? __ldg(ck + idx) : ck[idx]; w[r] = NC ? __ldg(cw + idx) : cw[idx]; }
+            off += __popc(m);
+        }
+#pragma unroll
+        for (int r = 0; r < RN; ++r) {
+            if (j0 + r < load) {
+                acc = add_rn(acc, mul_rn(q_s[e[r] & (kLastFlag - 1u)], w[r]));
+                if (e[r] & kLastFlag) { *res_cur = acc; res_cur += res_step; acc = (T)0; }
+            }
+        }
+    }
+    __syncwarp();
     T* ov = a.out.vals + slot;
     Sq128 sq = tot.sq;
     int nz = 0;
-    int c_n = 0, off_n = 0;
-    if (b0 < nb) {
-        const int p = (b0 << 5) + lane;
-        if (p < no) c_n = NC ? (int)__ldg(cnt + p) : (int)cnt[p];
-        off_n = NC ? __ldg(bptr + b0) : bptr[b0];
-    }
-    for (int b = b0; b < nb; b += bstride) {
-        const int p = (b << 5) + lane;
+    int ii = 0;
+    for (int c = g; c < nb; c += G, ++ii) {
+        const int p = (c << 5) + lane;
         const bool act = p < no;
-        const int c = c_n;
-        int off = off_n;
-        if (b + bstride < nb) {         // next block's counts while this one is summed
-            const int pn = ((b + bstride) << 5) + lane;
-            c_n = 0;
-            if (pn < no) c_n = NC ? (int)__ldg(cnt + pn) : (int)cnt[pn];
-            off_n = NC ? __ldg(bptr + b + bstride) : bptr[b + bstride];
-        }
-        const int maxc = __shfl_sync(kFull, c, 0);
-        T acc = (T)0;
-        if (SRC != kStaged) {
-            // global memory: the loads of kNumR rounds go out before the first of them is consumed
-            for (int j0 = 0; j0 < maxc; j0 += kNumR) {
-                unsigned kk[kNumR];
-                T ww[kNumR];
-#pragma unroll
-                for (int r = 0; r < kNumR; ++r) {
-                    const bool on = j0 + r < c;
-                    kk[r] = 0u; ww[r] = (T)0;
-                    if (on) { kk[r] = NC ? __ldg(ck + off + lane) : ck[off + lane]; ww[r] = NC ? __ldg(cw + off + lane) : cw[off + lane]; }
-                    off += __popc(__ballot_sync(kFull, on));
-                }
-#pragma unroll
-                for (int r = 0; r < kNumR; ++r)
-                    if (j0 + r < c) acc = add_rn(acc, mul_rn(q_s[kk[r]], ww[r]));
-            }
-        } else {
-            // shared memory: one round ahead is enough
-            unsigned k_n = 0u;
-            T w_n = (T)0;
-            if (c > 0) { k_n = ck[off + lane]; w_n = cw[off + lane]; }
-            for (int j = 0; j < maxc; ++j) {
-                const bool on = j < c;
-                const unsigned k = k_n;
-                const T w = w_n;
-                off += __popc(__ballot_sync(kFull, on));
-                if (j + 1 < c) { k_n = ck[off + lane]; w_n = cw[off + lane]; }
-                if (on) acc = add_rn(acc, mul_rn(q_s[k], w));
-            }
-        }
         T v = (T)0;
         if (act) {
-            v = mul_rn(a.scale, acc);
+            v = mul_rn(a.scale, res_s[(c << 5) + ((ii & 1) ? 31 - lane : lane)]);      // the lane that owned this position
             if (p == dpos) v = add_rn(v, a.restart);
             const T d = sub_rn(q_s[p], v);
             sq_add(sq, (double)d * (double)d);
@@ -267,80 +262,11 @@ __device__ __forceinline__ void numeric_blocks(const PropArgs<T>& a, const unsig
 }
 
 // ---------------------------------------------------------------------------------------------
-// The same numeric pass for a row staged in shared memory, U blocks of 32 outputs at a time: the sums of one output are
-// a chain of dependent additions, so the warp's only instruction-level parallelism is across blocks.  Blocks are sorted
-// by count, so the U blocks of an iteration have similar round counts (the first has the most).
-// ---------------------------------------------------------------------------------------------
-template <typename T, int U>
-__device__ __forceinline__ void numeric_staged(const PropArgs<T>& a, const unsigned char* blk, int no, int nprod, int dpos,
-                                               const T* q_s, long long slot, SelCtx<T>& sel, RowTotals& tot) {
-    const StructLayout L = struct_layout<T>(no, nprod);
-    const int32_t* bptr = reinterpret_cast<const int32_t*>(blk + L.bptr);
-    const uint16_t* cnt = reinterpret_cast<const uint16_t*>(blk + L.cnt);
-    const uint16_t* ck = reinterpret_cast<const uint16_t*>(blk + L.ck) + lane_id();
-    const T* cw = reinterpret_cast<const T*>(blk + L.cw) + lane_id();
-    const int lane = lane_id();
-    const int nb = (no + 31) >> 5;
-    T* ov = a.out.vals + slot;
-    Sq128 sq = tot.sq;
-    int nz = 0;
-    for (int b = 0; b < nb; b += U) {
-        int c[U], off[U];
-        T acc[U];
-        unsigned kn[U];
-        T wn[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int p = ((b + u) << 5) + lane;
-            c[u] = 0; off[u] = 0; acc[u] = (T)0; kn[u] = 0u; wn[u] = (T)0;
-            if (b + u < nb) {
-                if (p < no) c[u] = (int)cnt[p];
-                off[u] = bptr[b + u];
-            }
-        }
-        const int maxc = __shfl_sync(kFull, c[0], 0);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (c[u] > 0) { kn[u] = ck[off[u]]; wn[u] = cw[off[u]]; }
-        for (int j = 0; j < maxc; ++j) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool on = j < c[u];
-                const unsigned k = kn[u];
-                const T w = wn[u];
-                off[u] += __popc(__ballot_sync(kFull, on));
-                if (j + 1 < c[u]) { kn[u] = ck[off[u]]; wn[u] = cw[off[u]]; }
-                if (on) acc[u] = add_rn(acc[u], mul_rn(q_s[k], w));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (b + u < nb) {
-                const int p = ((b + u) << 5) + lane;
-                const bool act = p < no;
-                T v = (T)0;
-                if (act) {
-                    v = mul_rn(a.scale, acc[u]);
-                    if (p == dpos) v = add_rn(v, a.restart);
-                    const T d = sub_rn(q_s[p], v);
-                    sq_add(sq, (double)d * (double)d);
-                    ov[p] = v;
-                }
-                const bool nzv = act && v != (T)0;
-                sel.add(nzv, v);
-                nz += __popc(__ballot_sync(kFull, nzv));
-            }
-        }
-    }
-    tot.sq = sq;
-    if (lane == 0) tot.nnz += (unsigned long long)nz;
-}
-
-// ---------------------------------------------------------------------------------------------
-// The fast kernel: one warp per row, rows dealt round robin over a grid that fills the GPU once.  Every warp runs a
-// two-stage pipeline of its own: while row i is validated and summed out of shared memory, the bulk copies (TMA) of row
-// i + stride - its previous values and the hot part of its pool block - are in flight, completing on the stage's
-// mbarrier.  A row that does not fit a stage is read straight from global memory.
+// The fast kernel: one warp per short row (one group), rows dealt round robin over a grid that fills the GPU once.
+// Every warp runs a two-stage pipeline of its own: while row i is validated and summed out of shared memory, the bulk
+// copies (TMA) of row i + stride - its previous values and the hot part of its pool block - are in flight, completing
+// on the stage's mbarrier.  Long rows (several groups, or too large for a stage) belong to fast_big_kernel, which the
+// host queues in front of this kernel once it knows of such rows; until then they are replayed here from global memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFastStages = 2;
 struct FastShape {
@@ -355,8 +281,40 @@ __host__ __device__ inline FastShape fast_shape(int no_max, int hot_max) {
     f.no_max = no_max;
     f.hot_max = (hot_max + 15) & ~15;
     f.stage = align16((size_t)no_max * sizeof(T)) + (size_t)f.hot_max;
-    f.smem = (size_t)kFastWarps * kFastStages * f.stage + align16((size_t)kHistWin * 4);
+    // per warp: the stages and one array of sums
+    f.smem = (size_t)kFastWarps * (kFastStages * f.stage + align16((size_t)no_max * sizeof(T))) + align16((size_t)kHistWin * 4);
     return f;
+}
+// Shared memory of fast_big_kernel: previous values and sums of one row of up to no_max outputs, the select window.
+template <typename T>
+__host__ __device__ inline size_t big_smem_bytes(int no_max) {
+    return 2 * align16((size_t)no_max * sizeof(T)) + align16((size_t)kHistWin * 4);
+}
+
+// Validation of a row against its structure: the previous values (thresholded into q_s) must all lie inside K+.
+// `lanes`: the threads sharing the row (a warp or the CTA), `t` this thread's index among them.
+template <typename T>
+__device__ __forceinline__ bool stage_previous(const T* rv, const uint32_t* kbits, int no, T cut, T* q_s, int t, int lanes, int& nkept) {
+    bool bad = false;
+    for (int b = 0; b < no; b += 4 * lanes) {
+        T v[4];
+        unsigned kb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = b + u * lanes + t;
+            v[u] = (T)0; kb[u] = 0u;
+            if (p < no) { v[u] = rv[p]; kb[u] = kbits[p >> 5]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = b + u * lanes + t;
+            const bool kept = v[u] > cut;
+            if (kept && ((kb[u] >> (p & 31)) & 1u) == 0u) bad = true;
+            if (p < no) q_s[p] = kept ? v[u] : (T)0;
+            nkept += __popc(__ballot_sync(kFull, kept));
+        }
+    }
+    return bad;
 }
 
 template <typename T>
@@ -366,9 +324,11 @@ __global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArg
     __shared__ __align__(8) unsigned long long s_bar[kFastWarps][kFastStages];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    unsigned char* my = smem_raw + (size_t)warp * kFastStages * fs.stage;
-    unsigned int* win = reinterpret_cast<unsigned int*>(smem_raw + (size_t)kFastWarps * kFastStages * fs.stage);
     const size_t vals_bytes = align16((size_t)fs.no_max * sizeof(T));
+    const size_t per_warp = kFastStages * fs.stage + vals_bytes;
+    unsigned char* my = smem_raw + (size_t)warp * per_warp;
+    T* res_s = reinterpret_cast<T*>(my + kFastStages * fs.stage);
+    unsigned int* win = reinterpret_cast<unsigned int*>(smem_raw + (size_t)kFastWarps * per_warp);
     for (int i = threadIdx.x; i < kHistWin; i += blockDim.x) win[i] = 0u;
     if (threadIdx.x == 0) s_wn = 0u;
     if (lane == 0) {
@@ -385,19 +345,22 @@ __global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArg
     const int step = __ldcg(&st->step);
     SelCtx<T> sel = make_sel<T>(a, win, &s_wn);
     RowTotals tot = {{0ull, 0ull}, 0ull, 0ull, 0, 0};
-    int n_fast = 0;
+    int n_fast = 0, n_big = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->unordered_rows = 1;
 
     // what the pipeline keeps of a header; kind 0: no usable structure (slow list), 1: staged through shared memory,
-    // 2: read from global memory
-    struct Hdr { long long off, slot; int no, nprod, dpos, nk, hot, kind; };
+    // 2: replayed from global memory (a long row the big-row kernel has not taken), 3: already done this step
+    struct Hdr { long long off, slot; int no, nprod, dpos, nk, hot, groups, kind; };
     auto load_hdr = [&](int row) -> Hdr {
         const RowStruct r = a.rs[row];
         Hdr h;
         h.off = r.off; h.slot = r.slot; h.no = r.no; h.nprod = r.nprod; h.dpos = r.dpos; h.nk = r.nk; h.hot = r.hot_bytes;
+        h.groups = r.groups;
         h.kind = 0;
-        if (cut_on && r.gen == gen && gen != 0u && r.step == step - 1 && r.no > 0)
-            h.kind = (r.no <= fs.no_max && r.hot_bytes <= fs.hot_max) ? 1 : 2;
+        if (cut_on && r.gen == gen && gen != 0u && r.no > 0) {
+            if (r.step == step) h.kind = 3;
+            else if (r.step == step - 1) h.kind = (r.groups == 1 && r.no <= fs.no_max && r.hot_bytes <= fs.hot_max) ? 1 : 2;
+        }
         return h;
     };
     auto issue = [&](const Hdr& h, int g) {               // lane 0: the stage is free and behind a proxy fence
@@ -427,45 +390,29 @@ __global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArg
         const int kind = h.kind;
         unsigned char* stg = my + (size_t)g * fs.stage;
         T* q_s = reinterpret_cast<T*>(stg);
-        bool ok = kind != 0;
+        bool ok = kind == 1 || kind == 2;
         int nkept = 0;
         if (kind == 1) {
             mbar_wait(&s_bar[warp][g], (phase >> g) & 1u);
             phase ^= 1u << g;
         }
         if (ok) {
-            const StructLayout L = struct_layout<T>(h.no, h.nprod);
+            const StructLayout L = struct_layout<T>(h.no, h.nprod, h.groups);
             const uint32_t* kbits = kind == 1 ? reinterpret_cast<const uint32_t*>(stg + vals_bytes + L.kbits)
                                               : reinterpret_cast<const uint32_t*>(a.pool + h.off + L.kbits);
             const T* rv = kind == 1 ? q_s : a.in.vals + h.slot;
-            bool bad = false;
-            if (kind == 2 && h.no > fs.no_max) bad = true;          // no room for the previous values: rebuild (the symbolic kernel defers it)
-            else
-            for (int b = 0; b < h.no; b += 128) {
-                T v[4];
-                unsigned kb[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int p = b + u * 32 + lane;
-                    v[u] = (T)0; kb[u] = 0u;
-                    if (p < h.no) v[u] = rv[p];
-                    if (b + u * 32 < h.no) kb[u] = kbits[(b >> 5) + u];
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int p = b + u * 32 + lane;
-                    const bool kept = v[u] > cut;
-                    if (kept && ((kb[u] >> lane) & 1u) == 0u) bad = true;
-                    if (p < h.no) q_s[p] = kept ? v[u] : (T)0;
-                    nkept += __popc(__ballot_sync(kFull, kept));
-                }
-            }
+            bool bad = true;                                        // no room for the previous values: rebuild
+            if (h.no <= fs.no_max) bad = stage_previous<T>(rv, kbits, h.no, cut, q_s, lane, 32, nkept);
             ok = !__any_sync(kFull, bad);
         }
         if (ok) {
             __syncwarp();
-            if (kind == 1) numeric_staged<T, 2>(a, stg + vals_bytes, h.no, h.nprod, h.dpos, q_s, h.slot, sel, tot);
-            else numeric_blocks<T, kGlobalRO>(a, a.pool + h.off, h.no, h.nprod, h.dpos, q_s, h.slot, sel, tot, 0, 1);
+            if (kind == 1) numeric_stream<T, kStaged>(a, stg + vals_bytes, h.no, h.nprod, 1, 0, h.dpos, q_s, res_s, h.slot, sel, tot);
+            else {
+                for (int gg = 0; gg < h.groups; ++gg)
+                    numeric_stream<T, kGlobalRO>(a, a.pool + h.off, h.no, h.nprod, h.groups, gg, h.dpos, q_s, res_s, h.slot, sel, tot);
+                ++n_big;
+            }
             if (lane == 0) {
                 a.out.row_ptr[row] = h.slot;
                 a.out.row_len[row] = h.no;
@@ -475,7 +422,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArg
                 tot.max_kept = max(tot.max_kept, h.nk);
             }
             ++n_fast;
-        } else if (lane == 0) {
+        } else if (kind != 3 && lane == 0) {
             a.slow_list[atomicAdd(&st->slow_count, 1u)] = row;
         }
         // the stage is released: copies of the row after next, header of the one after that
@@ -491,6 +438,75 @@ __global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArg
     }
     pdl_launch_dependents();
     if (lane == 0 && n_fast) atomicAdd(&st->fast_rows, (unsigned)n_fast);
+    if (lane == 0 && n_big) atomicAdd(&st->big_rows, (unsigned)n_big);
+    publish_totals(st, tot);
+    sel.flush(st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Long rows: one CTA per row, one warp per group of the row.  The previous values are validated and thresholded into
+// shared memory by the whole CTA; every warp then replays its group's stream from global memory (read once, front to
+// back, kNumR rounds of loads in flight).  Rows this kernel takes are marked done for the step; the fast kernel that
+// follows skips them.  fs: the fast kernel's stage limits (a row that fits them is left to it).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBigGroups * 32) propagate_fast_big_kernel(PropArgs<T> a, FastShape fs, int NQ) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned int s_wn;
+    __shared__ int s_nkept;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int lane = lane_id();
+    const int warp = tid >> 5;
+    const int W = nth >> 5;
+    T* q_s = reinterpret_cast<T*>(smem_raw);
+    T* res_s = reinterpret_cast<T*>(smem_raw + align16((size_t)NQ * sizeof(T)));
+    unsigned int* win = reinterpret_cast<unsigned int*>(smem_raw + 2 * align16((size_t)NQ * sizeof(T)));
+    for (int i = tid; i < kHistWin; i += nth) win[i] = 0u;
+    if (tid == 0) s_wn = 0u;
+    pdl_wait();
+    WalkState* st = a.st;
+    if (st->done) return;
+    __syncthreads();
+    const bool cut_on = __ldcg(&st->cut_on) != 0;
+    const T cut = (T)__ldcg(&st->cut);
+    const unsigned gen = __ldcg(&st->pool_gen);
+    const int step = __ldcg(&st->step);
+    SelCtx<T> sel = make_sel<T>(a, win, &s_wn);
+    RowTotals tot = {{0ull, 0ull}, 0ull, 0ull, 0, 0};
+    int n_done = 0;
+    if (cut_on && gen != 0u)
+    for (int row = blockIdx.x; row < a.n_rows; row += gridDim.x) {
+        const RowStruct h = a.rs[row];
+        const bool mine = h.gen == gen && h.no > 0 && h.no <= NQ && h.step == step - 1 &&
+                          !(h.groups == 1 && h.no <= fs.no_max && h.hot_bytes <= fs.hot_max);
+        if (!mine) continue;                                    // (uniform over the CTA)
+        if (tid == 0) s_nkept = 0;
+        __syncthreads();
+        const StructLayout L = struct_layout<T>(h.no, h.nprod, h.groups);
+        int nkept = 0;
+        const bool bad = stage_previous<T>(a.in.vals + h.slot, reinterpret_cast<const uint32_t*>(a.pool + h.off + L.kbits), h.no, cut,
+                                           q_s, tid, nth, nkept);
+        if (lane == 0 && nkept) atomicAdd(&s_nkept, nkept);
+        if (__syncthreads_or(bad ? 1 : 0)) {
+            // the kept set left K+: the fast kernel finds the row neither current nor done and hands it to the symbolic kernel
+            if (tid == 0) a.rs[row].step = -2;
+            continue;
+        }
+        for (int g = warp; g < h.groups; g += W)
+            numeric_stream<T, kGlobalRO>(a, a.pool + h.off, h.no, h.nprod, h.groups, g, h.dpos, q_s, res_s, h.slot, sel, tot);
+        if (tid == 0) {
+            a.out.row_ptr[row] = h.slot;
+            a.out.row_len[row] = h.no;
+            a.rs[row].step = step;
+            tot.kept += (unsigned long long)s_nkept;
+            tot.max_len = max(tot.max_len, h.no);
+            tot.max_kept = max(tot.max_kept, h.nk);
+            ++n_done;
+        }
+        __syncthreads();
+    }
+    pdl_launch_dependents();
+    if (tid == 0 && n_done) { atomicAdd(&st->fast_rows, (unsigned)n_done); atomicAdd(&st->big_rows, (unsigned)n_done); }
     publish_totals(st, tot);
     sel.flush(st);
 }
@@ -506,8 +522,9 @@ __global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArg
 //   P4  the products into one staging list per output, IN STREAM ORDER: the operands are taken in windows of 32; the
 //       products of a window set their operand's bit in the output's window mask, a product's place is the output's
 //       fill level before the window plus the number of lower bits in the mask
-//   P5  pool block: the lists of a block's 32 outputs interleaved round by round; fixed slot; header
-//   P6  numeric pass, fused into P5: the lane that copies an output's list also sums it
+//   P5  pool block: the outputs dealt to groups and lanes, the lanes' products written as the groups' streams (the
+//       writer walks the rounds exactly as the reader will); fixed slot; header
+//   P6  numeric pass, fused into P5: the lane that copies a product also adds it
 // Nothing depends on the order in which threads run, except the order of the outputs inside a count class (arbitrary;
 // it only decides where a value is stored, never its bits).
 // ---------------------------------------------------------------------------------------------
@@ -528,7 +545,7 @@ __host__ __device__ inline size_t sym_smem_bytes(int H, int no_max, int km, int 
            align16((size_t)km * 2) * 2 +                              // kslot, kpos
            align16((size_t)no_max * 2) * 3 +                          // olist, oslot, cnt_s
            align16((size_t)no_max * 4) +                              // cptr
-           align16((size_t)no_max * s) +                              // q_s
+           align16((size_t)no_max * s) * 2 +                          // q_s, res_s
            align16((nbm + 1) * 4) * 2 +                               // bptr_s, kb_s
            align16((size_t)tmp_smem * 2) * 3 + align16((size_t)tmp_smem * s) +   // pslot, pk, tck, tcw
            align16((size_t)kHistWin * 4);                             // select window
@@ -540,10 +557,12 @@ __host__ __device__ inline size_t sym_tmp_bytes(int tmp_cap, size_t s) {        
 __device__ __forceinline__ uint32_t sym_hash(int32_t j, int mask) { return (((uint32_t)j * 0x9E3779B1u) >> 7) & (uint32_t)mask; }
 
 template <typename T>
-__global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape sh) {
+__global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape sh) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned int s_wn;
     __shared__ int s_nk, s_nkt, s_nout, s_nprod;
+    __shared__ uint16_t lload_s[32 * kBigGroups];
+    __shared__ int32_t gptr_s[kBigGroups + 1];
     __shared__ unsigned long long s_slot_base, s_slot_left, s_pool_base, s_pool_left, s_slot_rel, s_poff;
     const int tid = threadIdx.x, nth = blockDim.x;
     const int lane = lane_id();
@@ -568,6 +587,7 @@ __global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape s
     uint16_t* cnt_s = reinterpret_cast<uint16_t*>(p);   p += align16((size_t)NOMAX * 2);
     int32_t* cptr = reinterpret_cast<int32_t*>(p);      p += align16((size_t)NOMAX * 4);
     T* q_s = reinterpret_cast<T*>(p);                   p += align16((size_t)NOMAX * s);
+    T* res_s = reinterpret_cast<T*>(p);                 p += align16((size_t)NOMAX * s);
     const size_t nbm = (size_t)(NOMAX + 31) / 32;
     int32_t* bptr_s = reinterpret_cast<int32_t*>(p);    p += align16((nbm + 1) * 4);
     uint32_t* kb_s = reinterpret_cast<uint32_t*>(p);    p += align16((nbm + 1) * 4);
@@ -595,7 +615,7 @@ __global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape s
     const int n_list = a.row_list_count ? (int)__ldcg(a.row_list_count) : a.n_rows;
     SelCtx<T> sel = make_sel<T>(a, win, &s_wn);
     RowTotals tot = {{0ull, 0ull}, 0ull, 0ull, 0, 0};
-    int n_built = 0;
+    int n_built = 0, n_big = 0;
     long long hot_delta = 0;
     if (blockIdx.x == 0 && tid == 0) {
         st->unordered_rows = 1;
@@ -681,10 +701,17 @@ __global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape s
         bool defer = nk > KM;
         int no = 0, nprod = 0;
         if (!defer) {
+            // (kcol_u is padded to a multiple of four with a column no real one is below)
+            for (int i = nk + tid; i < ((nk + 3) & ~3); i += nth) kcol_u[i] = 0x7fffffff;
+            __syncthreads();
             for (int i = tid; i < nk; i += nth) {
                 const int32_t c = kcol_u[i];
                 int r = 0;
-                for (int j = 0; j < nk; ++j) r += (kcol_u[j] < c) ? 1 : 0;
+                const int4* q4 = reinterpret_cast<const int4*>(kcol_u);
+                for (int j = 0; j < (nk + 3) >> 2; ++j) {
+                    const int4 v = q4[j];
+                    r += (v.x < c) + (v.y < c) + (v.z < c) + (v.w < c);
+                }
                 kcol[r] = c;
                 kval[r] = kval_u[i];
                 const int ps = __ldg(a.p_indptr + c);
@@ -721,21 +748,20 @@ __global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape s
             // ---- P2: the output set and the products per output
             for (int i = tid; i < nk; i += nth) kslot[i] = (uint16_t)insert(kcol[i]);
             if (tid == 0) insert(dcol);
-            for (int i = tid; i < nprod; i += nth) {
-                int lo = 0, hi = nk - 1;                    // operand of product i: kpre[k] <= i < kpre[k + 1]
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (kpre[mid + 1] <= i) lo = mid + 1; else hi = mid;
+            // a warp per operand: its P row is read coalesced; product i = kpre[k] + e of the stream
+            for (int k = warp; k < nk; k += W) {
+                const int ps = kps[k], i0 = kpre[k], ln = kpre[k + 1] - i0;
+                for (int e = lane; e < ln; e += 32) {
+                    int sl = 0;
+                    if (s_nout <= NOMAX) {
+                        const int32_t j = __ldg(pcols + ps + e);
+                        CRWR_CHECK(st, j >= 0, 5);
+                        sl = insert(j);
+                        atomicAdd(&hcnt[sl], 1);
+                    }
+                    pslot[i0 + e] = (uint16_t)sl;
+                    pk[i0 + e] = (uint16_t)k;
                 }
-                int sl = 0;
-                if (s_nout <= NOMAX) {
-                    const int32_t j = __ldg(pcols + kps[lo] + (i - kpre[lo]));
-                    CRWR_CHECK(st, j >= 0, 5);
-                    sl = insert(j);
-                    atomicAdd(&hcnt[sl], 1);
-                }
-                pslot[i] = (uint16_t)sl;
-                pk[i] = (uint16_t)lo;
             }
             __syncthreads();
             no = s_nout;
@@ -804,7 +830,10 @@ __global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape s
             CRWR_CHECK(st, bptr_s[nb] == nprod, 8);
         }
         unsigned long long slot_rel = 0, poff = 0;
-        const StructLayout L = struct_layout<T>(no, nprod);
+        // a row the fast kernel cannot stage in shared memory is dealt to several groups (a CTA replays it)
+        int G = 1;
+        if (no > a.small_no || struct_layout<T>(no, nprod, 1).hot_bytes > (uint32_t)a.small_hot) G = kBigGroups;
+        const StructLayout L = struct_layout<T>(no, nprod, G);
         const unsigned long long no4 = (unsigned long long)((no + 3) & ~3);     // slots start on 16-byte boundaries (bulk copies)
         if (!defer) {
             // ---- reservations: fixed slot in both iterate buffers, pool block (thread 0; chunked while many rows are built)
@@ -880,56 +909,92 @@ __global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape s
             }
             __syncthreads();
         }
-        // ---- P5: the pool block; the staging lists interleaved round by round; the slot's columns (written once)
-        {
-            int32_t* ocols_w = reinterpret_cast<int32_t*>(blk + L.ocols);
-            int32_t* bptr_w = reinterpret_cast<int32_t*>(blk + L.bptr);
-            uint32_t* kbits_w = reinterpret_cast<uint32_t*>(blk + L.kbits);
-            uint16_t* cnt_w = reinterpret_cast<uint16_t*>(blk + L.cnt);
-            uint16_t* ck_w = reinterpret_cast<uint16_t*>(blk + L.ck);
-            T* cw_w = reinterpret_cast<T*>(blk + L.cw);
-            for (int i = tid; i <= nb; i += nth) bptr_w[i] = bptr_s[i];
-            for (int i = tid; i < nb; i += nth) kbits_w[i] = kb_s[i];
-            for (int b = warp; b < nb; b += W) {
-                const int pp = (b << 5) + lane;
-                int c = 0, src = 0;
-                if (pp < no) {
-                    const int sl = oslot[pp];
-                    const int32_t col = hkey[sl];
-                    c = (int)cnt_s[pp];
-                    src = bptr_s[b] + cptr[pp];
-                    ocols_w[pp] = col;
-                    cnt_w[pp] = (uint16_t)c;
-                    a.in.cols[slot + pp] = col;
-                    a.out.cols[slot + pp] = col;
-                }
-                int off = bptr_s[b];
-                const int maxc = __shfl_sync(kFull, c, 0);
-                T acc = (T)0;
-                for (int j = 0; j < maxc; ++j) {
-                    const bool on = j < c;
-                    if (on) {
-                        const unsigned k = tck[src + j];
-                        const T w = tcw[src + j];
-                        ck_w[off + lane] = (uint16_t)k;
-                        cw_w[off + lane] = w;
-                        acc = add_rn(acc, mul_rn(q_s[k], w));        // P6: the numeric pass, on the way
-                    }
-                    off += __popc(__ballot_sync(kFull, on));
-                }
-                T v = (T)0;
-                if (pp < no) {
-                    v = mul_rn(a.scale, acc);
-                    if (pp == dpos) v = add_rn(v, a.restart);
-                    const T d = sub_rn(q_s[pp], v);
-                    sq_add(tot.sq, (double)d * (double)d);
-                    a.out.vals[slot + pp] = v;
-                }
-                const bool nzv = pp < no && v != (T)0;
-                sel.add(nzv, v);
-                const int nzc = __popc(__ballot_sync(kFull, nzv));
-                if (lane == 0) tot.nnz += (unsigned long long)nzc;
+        // ---- P5: the lanes' shares (chunk by chunk, alternating direction), the group streams, the slot's columns
+        // (written once, both buffers); P6, the numeric pass, on the way: the lane that copies a product also adds it
+        int32_t* ocols_w = reinterpret_cast<int32_t*>(blk + L.ocols);
+        uint16_t* lload_w = reinterpret_cast<uint16_t*>(blk + L.lload);
+        int32_t* gptr_w = reinterpret_cast<int32_t*>(blk + L.gptr);
+        uint32_t* kbits_w = reinterpret_cast<uint32_t*>(blk + L.kbits);
+        uint16_t* ck_w = reinterpret_cast<uint16_t*>(blk + L.ck);
+        T* cw_w = reinterpret_cast<T*>(blk + L.cw);
+        for (int g = warp; g < G; g += W) {
+            int sum = 0;
+            for (int ii = 0; ii * G + g < nb; ++ii) {
+                const int pp = lane_pos(ii, g, G, lane);
+                if (pp < no) sum += (int)cnt_s[pp];
             }
+            lload_s[g * 32 + lane] = (uint16_t)sum;
+            CRWR_CHECK(st, sum < 65536, 10);
+            const int gsum = __reduce_add_sync(kFull, sum);
+            if (lane == 0) gptr_s[g + 1] = gsum;
+        }
+        for (int pp = tid; pp < no; pp += nth) {
+            const int32_t col = hkey[oslot[pp]];
+            ocols_w[pp] = col;
+            a.in.cols[slot + pp] = col;
+            a.out.cols[slot + pp] = col;
+            res_s[pp] = (T)0;
+        }
+        for (int i = tid; i < nb; i += nth) kbits_w[i] = kb_s[i];
+        __syncthreads();
+        if (tid == 0) {
+            gptr_s[0] = 0;
+            for (int g = 0; g < G; ++g) gptr_s[g + 1] += gptr_s[g];
+            CRWR_CHECK(st, gptr_s[G] == nprod, 11);
+        }
+        __syncthreads();
+        for (int i = tid; i < 32 * G; i += nth) lload_w[i] = lload_s[i];
+        for (int i = tid; i <= G; i += nth) gptr_w[i] = gptr_s[i];
+        for (int g = warp; g < G; g += W) {
+            const int load = (int)lload_s[g * 32 + lane];
+            const int rounds = __reduce_max_sync(kFull, load);
+            int off = gptr_s[g];
+            int ii = 0, c = 0;
+            int pp = lane_pos(0, g, G, lane);
+            int cntp = pp < no ? (int)cnt_s[pp] : 0;
+            int src = pp < no ? bptr_s[pp >> 5] + cptr[pp] : 0;
+            T acc = (T)0;
+            for (int j = 0; j < rounds; ++j) {
+                const bool on = j < load;
+                const unsigned m = __ballot_sync(kFull, on);
+                if (on) {
+                    const int idx = off + __popc(m & lanemask_lt());
+                    const unsigned k = tck[src + c];
+                    const T w = tcw[src + c];
+                    const bool last = c + 1 == cntp;
+                    ck_w[idx] = (uint16_t)(k | (last ? kLastFlag : 0u));
+                    cw_w[idx] = w;
+                    acc = add_rn(acc, mul_rn(q_s[k], w));
+                    if (last) {
+                        res_s[pp] = acc;
+                        acc = (T)0;
+                        ++ii; c = 0;
+                        pp = lane_pos(ii, g, G, lane);
+                        const bool have = ii * G + g < nb && pp < no;
+                        cntp = have ? (int)cnt_s[pp] : 0;
+                        src = have ? bptr_s[pp >> 5] + cptr[pp] : 0;
+                    } else ++c;
+                }
+                off += __popc(m);
+            }
+            __syncwarp();
+            int nz = 0;
+            for (int ch = g; ch < nb; ch += G) {
+                const int q = (ch << 5) + lane;
+                const bool act = q < no;
+                T v = (T)0;
+                if (act) {
+                    v = mul_rn(a.scale, res_s[q]);
+                    if (q == dpos) v = add_rn(v, a.restart);
+                    const T d = sub_rn(q_s[q], v);
+                    sq_add(tot.sq, (double)d * (double)d);
+                    a.out.vals[slot + q] = v;
+                }
+                const bool nzv = act && v != (T)0;
+                sel.add(nzv, v);
+                nz += __popc(__ballot_sync(kFull, nzv));
+            }
+            if (lane == 0) tot.nnz += (unsigned long long)nz;
         }
         __syncthreads();
         // the table is released; header
@@ -937,7 +1002,7 @@ __global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape s
         if (tid == 0) {
             RowStruct hd;
             hd.off = (long long)poff; hd.slot = slot; hd.no = no; hd.nprod = nprod; hd.nk = nk; hd.dpos = dpos;
-            hd.gen = gen; hd.step = step; hd.hot_bytes = (int32_t)L.hot_bytes; hd.pad = 0;
+            hd.gen = gen; hd.step = step; hd.hot_bytes = (int32_t)L.hot_bytes; hd.groups = G;
             a.rs[row] = hd;
             a.out.row_ptr[row] = slot;
             a.out.row_len[row] = no;
@@ -945,6 +1010,7 @@ __global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape s
             tot.max_len = max(tot.max_len, no);
             tot.max_kept = max(tot.max_kept, nk);
             hot_delta += (long long)L.hot_bytes;
+            if (G > 1) ++n_big;
         }
         ++n_built;
         __syncthreads();
@@ -953,6 +1019,7 @@ __global__ void __launch_bounds__(256) symbolic_kernel(PropArgs<T> a, SymShape s
     pdl_launch_dependents();
     if (tid == 0 && n_built) atomicAdd(&st->built_rows, (unsigned)n_built);
     if (tid == 0 && hot_delta) atomicAdd(&st->hot_sum, (unsigned long long)hot_delta);
+    if (tid == 0 && n_big) atomicAdd(&st->big_rows, (unsigned)n_big);
     publish_totals(st, tot);
     sel.flush(st);
 }

@@ -112,7 +112,12 @@ def test_walk_matches_reference(cuda_device, name, tag, dtype):
 @pytest.mark.parametrize("name", ["bundled_m120_t80_rp50", "bundled_m250_t50_rp50", "synth1500_t80_rp50", "synth1500_t50_rp30",
                                   "synth3000dense_t80_rp50", "asym400_t60_rp50", "bundled_m120_t80_rp30"])
 @pytest.mark.parametrize("tag,dtype", [("64", np.float64), ("32", np.float32)])
-def test_bit_identity_with_reference_walk(cuda_device, name, tag, dtype):
+@pytest.mark.parametrize("structures", ["auto", "always"])
+def test_bit_identity_with_reference_walk(cuda_device, name, tag, dtype, structures, monkeypatch):
+    """Both propagation forms - the hash-accumulating row-group kernel and the cached-structure kernels (symbolic /
+    numeric split, which rows this short only take when forced) - against the vectors of the unmodified reference."""
+    if structures == "always":
+        monkeypatch.setenv("CRWR_STRUCT", "2")
     rec = load_golden(name)
     P = _P_from_golden(rec, dtype)
     Q = pkg.random_walk_b200(P, float(rec["rp"]), int(rec["perc"]), 0.01, len(rec["marker_idx"]), device=cuda_device)
@@ -419,9 +424,10 @@ def test_cached_structures_and_window_select_change_no_bit(cuda_device, dtype, m
     """The settled walk runs on the cached-structure kernel and the window select; with both switched off (row-group
     kernel and histogram select every step) the iterate, the cuts and the deltas are the same bits."""
     M, idx = synth.make_workload(synth.Workload("cs", 6000, 960, 100, 16))
+    monkeypatch.setenv("CRWR_STRUCT", "2")          # rows this short do not get structures by default
     steps, it, tr, _ = _walk(M, idx, dtype, cuda_device)
-    assert sum(t["fast_rows"] for t in tr[3:]) > 0.8 * idx.size * (len(tr) - 4)       # most rows, most steps
-    assert tr[1]["fast_rows"] == 0 and tr[2]["fast_rows"] == 0
+    assert sum(t["fast_rows"] for t in tr[4:]) > 0.8 * idx.size * (len(tr) - 5)       # most rows, most steps
+    assert all(tr[i]["fast_rows"] == 0 for i in range(4))
     monkeypatch.setenv("CRWR_STRUCT", "0")
     monkeypatch.setenv("CRWR_WIN_STEP", "0")
     steps0, it0, tr0, _ = _walk(M, idx, dtype, cuda_device)
@@ -438,6 +444,7 @@ def test_cached_structures_and_window_select_change_no_bit(cuda_device, dtype, m
 def test_structure_and_window_corner_policies_change_no_bit(cuda_device, env, monkeypatch):
     M, idx = synth.make_workload(synth.Workload("cs", 5000, 800, 100, 16))
     steps0, it0, tr0, _ = _walk(M, idx, np.float32, cuda_device)
+    monkeypatch.setenv("CRWR_STRUCT", "2")
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     steps, it, tr, _ = _walk(M, idx, np.float32, cuda_device)
