@@ -76,6 +76,10 @@ _SIGNATURES = {
     "crwr_peer_attach": (C.c_int32, [_P, _P, C.c_int32, C.c_uint64]),
     "crwr_step_peer_scan": (C.c_int32, [_P, C.c_int32, _P]),
     "crwr_step_peer_finish": (C.c_int32, [_P, _P]),
+    "crwr_step_window": (C.c_int32, [_P]),
+    "crwr_step_peer_tail": (C.c_int32, [_P, _P]),
+    "crwr_walk_redo": (C.c_int32, [_P, _P]),
+    "crwr_walk_enqueue_peer": (C.c_int32, [_P, C.c_int32, _P]),
     "crwr_walk_poll": (C.c_int32, [_P, C.POINTER(Status), _P]),
     "crwr_walk_trace": (C.c_int32, [_P, C.POINTER(StepRecord), C.c_int32, _P]),
     "crwr_result_count": (C.c_int32, [_P, C.POINTER(C.c_int64), _P]),

@@ -235,7 +235,10 @@ struct crwr_handle_s {
     long long struct_min_row = 256;             // ... mean stored entries per row from which they pay (CRWR_STRUCT_MIN_ROW)
     long long mean_row = 0;                     // mean stored entries per row at the last poll
     bool structs_active = false;                // this walk's decision, taken when the first structure step is queued
+    bool redo_hist = false;                     // sharded walk: the next step repeats one whose window missed (histogram select)
     int win_step = 6;                           // first walk step whose cut comes from the window select (CRWR_WIN_STEP; 0: never)
+    bool sharded_window_ok = false;             // sharded walk: the last poll saw a window narrow enough for the push regions
+    int win_step_sharded = 9;
     float alpha = 0.5f;                         // K+ = entries above alpha x cut (CRWR_STRUCT_ALPHA)
     float win_scale = 2.5f, win_min = 0.004f, win_max = 0.15f, win_rel_max = 0.10f;
     bool dense_always = false;                  // a step deferred rows while no large-row kernel was queued: always queue it
@@ -545,7 +548,9 @@ void launch_scan_i32(crwr_handle_s* h, const int32_t* cnt, int32_t* out, long lo
 // rows (673 -> 700 us; CTAs parked in pdl_wait share the SMs with long-running predecessors), so it is used for
 // short rows only.  CRWR_PDL=0/1 forces it off/on.
 bool use_pdl(const crwr_handle_s* h) {
-    if (h->cfg.n_shards != 1) return false;
+    // (sharded walks: only the peer-attached chain - its barrier kernels wait for their predecessor like everybody
+    // else; the host-driven collectives of the other path sit between the kernels anyway)
+    if (h->cfg.n_shards != 1 && !h->peer_attached) return false;
     if (h->pdl_forced >= 0) return h->pdl_forced != 0;
     return h->hint_len_eff <= 384;
 }
@@ -647,8 +652,10 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, bool win_step, cu
     }
     const int rows = a.n_rows;
     const bool pdl = use_pdl(h);
+    // (a sharded walk may have to run a step twice - peer.cuh, window miss - which a freshly rebuilt structure cannot)
     if (step == h->build_step)
-        h->structs_active = h->struct_mode == 2 || (h->struct_mode == 1 && h->mean_row >= h->struct_min_row);
+        h->structs_active = h->cfg.n_shards == 1 &&
+                            (h->struct_mode == 2 || (h->struct_mode == 1 && h->mean_row >= h->struct_min_row));
     const bool structs = h->structs_active && h->prop_kind == 1 && step >= h->build_step && h->fast_no > 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
@@ -777,9 +784,10 @@ FinishArgs finish_args(crwr_handle_s* h, int do_select, const void* gathered) {
     a.trace = h->at<crwr_step_record>(L.trace);
     a.do_select = do_select;
     // the step after this one is a window-select step: derive its window from this step's cut
-    a.next_win = (h->win_step > 0 && h->cfg.n_shards == 1 && h->steps_enqueued + 1 >= h->win_step) ? 1 : 0;
+    a.next_win = (h->win_step > 0 && (h->cfg.n_shards == 1 || h->peer_attached) && h->steps_enqueued + 1 >= h->win_step) ? 1 : 0;
     a.dense_launched = h->dense_launched ? 1 : 0;
     a.win_scale = h->win_scale; a.win_min = h->win_min; a.win_max = h->win_max; a.win_rel_max = h->win_rel_max;
+    a.win_narrow_cands = (long long)h->cfg.n_shards * (kPushCand * 3 / 4);
     return a;
 }
 
@@ -1014,6 +1022,8 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     if (h->build_step < 2) h->build_step = 2;       // structures only exist behind a cut
     h->win_step = env_int("CRWR_WIN_STEP", 6);
     if (h->win_step > 0 && h->win_step < 2) h->win_step = 2;
+    h->win_step_sharded = env_int("CRWR_WIN_STEP_SHARDED", 9);
+
     if (h->prop_kind != 1) h->win_step = 0;         // the warp-per-row kernel only knows the histogram select
     h->alpha = (float)env_double("CRWR_STRUCT_ALPHA", 0.5);
     if (!(h->alpha > 0.f && h->alpha <= 1.f)) h->alpha = 0.5f;
@@ -1158,6 +1168,8 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     h->avg_hot = 0;
     h->mean_row = 0;
     h->structs_active = false;
+    h->sharded_window_ok = false;
+    h->redo_hist = false;
     h->big_seen = false;
     h->fb_seen = false;
     h->dense_launched = true;
@@ -1325,13 +1337,25 @@ int32_t crwr_walk_enqueue(crwr_handle h, int32_t n_steps, void* stream) {
     const int parity = h->steps_enqueued & 1;                                             \
     (void)parity; (void)f64;
 
+// A sharded step takes the window select (one cross-GPU synchronisation, crwr_step_peer_tail) once the walk has settled.
+// The candidates of every rank must fit its push regions, so the window has to be narrow: from walk step
+// win_step_sharded on (the cut has nearly settled by then; CRWR_WIN_STEP_SHARDED), or earlier when a poll has seen a
+// narrow window already.  The state is replicated, so every rank switches in the same step; a window that turns out too
+// wide is a miss like any other (the step is repeated the three-barrier way).
+static bool sharded_window_step(const crwr_handle_s* h) {
+    return h->peer_attached && h->win_step > 0 && h->steps_enqueued >= h->win_step && !h->redo_hist &&
+           (h->sharded_window_ok || h->steps_enqueued >= h->win_step_sharded);
+}
+int32_t crwr_step_window(crwr_handle h) { return (h && h->walking && sharded_window_step(h)) ? 1 : 0; }
+
 int32_t crwr_step_propagate(crwr_handle h, void* stream) {
     STEP_PROLOGUE();
     // steps >= 1: the level-0 histogram is filled by the propagate epilogue (crwr_step_hist(0) then has nothing to do)
     h->hist0_fused = h->steps_enqueued >= 1;
-    int e = f64 ? launch_propagate<double>(h, parity, false, false, st) : launch_propagate<float>(h, parity, false, false, st);
+    const bool win = sharded_window_step(h);
+    int e = f64 ? launch_propagate<double>(h, parity, false, win, st) : launch_propagate<float>(h, parity, false, win, st);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "propagate launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if (!h->peer_attached) {        // with the peer exchange the counters are published by crwr_step_peer_scan
+    if (!h->peer_attached) {        // with the peer exchange the counters are published by crwr_step_peer_scan / _tail
         pack_exchange_kernel<<<1, 32, 0, st>>>(h->at<WalkState>(h->L.state), xbuf_ptr(h));
         LAUNCH_CHECK();
     }
@@ -1377,8 +1401,10 @@ int32_t crwr_peer_attach(crwr_handle h, void* d_block_ptrs, int32_t rank, uint64
     if (h->cfg.n_shards < 2 || h->cfg.n_shards > kPeerFlags) CRWR_FAIL(CRWR_ERR_INVALID, "peer exchange needs 2..%d shards", kPeerFlags);
     if (rank < 0 || rank >= h->cfg.n_shards) CRWR_FAIL(CRWR_ERR_INVALID, "rank out of range");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    unsigned long long* mine = nullptr;
-    CUDA_TRY(cudaMemcpy(&mine, (unsigned long long**)d_block_ptrs + rank, sizeof(mine), cudaMemcpyDeviceToHost));
+    // (the own block's address is read back once per pointer array: the copy synchronises the device)
+    unsigned long long* mine = h->peer_block;
+    if (!(h->peer_attached && h->peer.blocks == (unsigned long long* const*)d_block_ptrs && h->peer.rank == rank))
+        CUDA_TRY(cudaMemcpy(&mine, (unsigned long long**)d_block_ptrs + rank, sizeof(mine), cudaMemcpyDeviceToHost));
     h->peer.blocks = (unsigned long long* const*)d_block_ptrs;
     h->peer.world = h->cfg.n_shards;
     h->peer.rank = rank;
@@ -1395,8 +1421,8 @@ int32_t crwr_step_peer_scan(crwr_handle h, int32_t level, void* stream) {
     if (level < -1 || level >= kSelectLevels) CRWR_FAIL(CRWR_ERR_INVALID, "level out of range");
     const unsigned long long epoch = h->peer_epoch_base + 3ull * (unsigned long long)h->steps_enqueued + (level == 1 ? 2ull : 1ull);
     unsigned long long* local = h->at<unsigned long long>(h->L.xbuf);
-    if (f64) peer_scan_kernel<double><<<1, 1024, 0, st>>>(h->at<WalkState>(h->L.state), h->peer, local, level, epoch);
-    else peer_scan_kernel<float><<<1, 1024, 0, st>>>(h->at<WalkState>(h->L.state), h->peer, local, level, epoch);
+    if (f64) launch_k(use_pdl(h), peer_scan_kernel<double>, 1, 1024, 0, st, h->at<WalkState>(h->L.state), h->peer, local, level, epoch);
+    else launch_k(use_pdl(h), peer_scan_kernel<float>, 1, 1024, 0, st, h->at<WalkState>(h->L.state), h->peer, local, level, epoch);
     LAUNCH_CHECK();
     return CRWR_OK;
 }
@@ -1410,10 +1436,66 @@ int32_t crwr_step_peer_finish(crwr_handle h, void* stream) {
     FinishArgs a = finish_args(h, do_select, nullptr);
     a.xch = h->at<unsigned long long>(h->L.xbuf);         // local buffer: holds the sums peer_scan stored
     unsigned long long* gathered = h->at<unsigned long long>(h->L.gathered);
-    if (f64) peer_finish_kernel<double><<<1, 1024, 0, st>>>(a, h->peer, gathered, step & 1, epoch);
-    else peer_finish_kernel<float><<<1, 1024, 0, st>>>(a, h->peer, gathered, step & 1, epoch);
+    if (f64) launch_k(use_pdl(h), peer_finish_kernel<double>, 1, 1024, 0, st, a, h->peer, gathered, step & 1, epoch);
+    else launch_k(use_pdl(h), peer_finish_kernel<float>, 1, 1024, 0, st, a, h->peer, gathered, step & 1, epoch);
     LAUNCH_CHECK();
     h->steps_enqueued += 1;
+    h->redo_hist = false;
+    return CRWR_OK;
+}
+
+// Window-select step of a sharded walk: push + one flag barrier + select + finish (peer.cuh).
+int32_t crwr_step_peer_tail(crwr_handle h, void* stream) {
+    STEP_PROLOGUE();
+    if (!h->peer_attached) CRWR_FAIL(CRWR_ERR_STATE, "crwr_peer_attach first");
+    if (!sharded_window_step(h)) CRWR_FAIL(CRWR_ERR_STATE, "not a window step (crwr_step_window)");
+    const int step = h->steps_enqueued;
+    // the push exchange has flags of its own; one epoch per step
+    const unsigned long long epoch = h->peer_epoch_base + (unsigned long long)step + 1ull;
+    FinishArgs a = finish_args(h, 1, nullptr);
+    unsigned long long* local = h->at<unsigned long long>(h->L.xbuf);
+    if (f64) launch_k(use_pdl(h), peer_tail_kernel<double>, 1, 1024, 0, st, a, h->peer, local, cand_ptr(h, step), cand_ptr(h, step + 1), step & 1, epoch);
+    else launch_k(use_pdl(h), peer_tail_kernel<float>, 1, 1024, 0, st, a, h->peer, local, cand_ptr(h, step), cand_ptr(h, step + 1), step & 1, epoch);
+    LAUNCH_CHECK();
+    h->steps_enqueued += 1;
+    return CRWR_OK;
+}
+
+// After a poll that reported a window miss (crwr_status.capacity_overflow bit 2): the walk goes on, the missed step is
+// queued again with the histogram select (crwr_step_window answers 0 for it).
+int32_t crwr_walk_redo(crwr_handle h, void* stream) {
+    if (!h || !h->walking) CRWR_FAIL(CRWR_ERR_STATE, "crwr_walk_init first");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    peer_redo_kernel<<<1, 32, 0, st>>>(h->at<WalkState>(h->L.state));
+    LAUNCH_CHECK();
+    h->redo_hist = true;
+    return CRWR_OK;
+}
+
+// n_steps whole steps of a peer-attached shard in one call (what a host loop over the crwr_step_* calls does).
+int32_t crwr_walk_enqueue_peer(crwr_handle h, int32_t n_steps, void* stream) {
+    if (!h || !h->walking) CRWR_FAIL(CRWR_ERR_STATE, "crwr_walk_init first");
+    if (!h->peer_attached) CRWR_FAIL(CRWR_ERR_STATE, "crwr_peer_attach first");
+    for (int i = 0; i < n_steps; ++i) {
+        int32_t rc = CRWR_OK;
+        if (sharded_window_step(h)) {
+            if ((rc = crwr_step_propagate(h, stream)) != CRWR_OK) return rc;
+            if ((rc = crwr_step_peer_tail(h, stream)) != CRWR_OK) return rc;
+            continue;
+        }
+        const bool first = h->steps_enqueued == 0;
+        if ((rc = crwr_step_propagate(h, stream)) != CRWR_OK) return rc;
+        if (first) {
+            if ((rc = crwr_step_peer_scan(h, -1, stream)) != CRWR_OK) return rc;
+        } else {
+            if ((rc = crwr_step_peer_scan(h, 0, stream)) != CRWR_OK) return rc;
+            if ((rc = crwr_step_hist(h, 1, stream)) != CRWR_OK) return rc;
+            if ((rc = crwr_step_peer_scan(h, 1, stream)) != CRWR_OK) return rc;
+            if ((rc = crwr_step_gather(h, stream)) != CRWR_OK) return rc;
+        }
+        if ((rc = crwr_step_peer_finish(h, stream)) != CRWR_OK) return rc;
+    }
     return CRWR_OK;
 }
 
@@ -1440,15 +1522,16 @@ int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
     CUDA_TRY(cudaStreamSynchronize(st));
     const WalkState& s = *h->h_state;
     out->steps_done = s.step;
-    out->stop_reason = s.done ? s.stop_reason : CRWR_STOP_RUNNING;
-    out->capacity_overflow = s.capacity_overflow | (s.select_overflow << 1);
+    out->stop_reason = (s.done && !s.win_missed) ? s.stop_reason : CRWR_STOP_RUNNING;
+    out->capacity_overflow = s.capacity_overflow | (s.select_overflow << 1) | (s.win_missed << 2);
+    h->sharded_window_ok = s.win_on != 0 && s.win_narrow != 0;
     out->fallback_rows = s.last_fallback_rows;
     out->nnz_iterate = (int64_t)s.nnz_exact;
     out->max_row_len = s.last_max_row_len;
     out->max_kept = s.last_max_kept;
     out->last_cut = s.cut;
     out->last_delta = s.last_delta;
-    if (s.done && s.stop_reason == CRWR_STOP_RUNNING) out->stop_reason = CRWR_STOP_MAX_STEPS;
+    if (s.done && !s.win_missed && s.stop_reason == CRWR_STOP_RUNNING) out->stop_reason = CRWR_STOP_MAX_STEPS;
     // the host-side step counter follows the device: steps enqueued past the stop were skipped
     if (s.done) h->steps_enqueued = s.step;
     if (s.last_fallback_rows > 0) h->fb_seen = true;

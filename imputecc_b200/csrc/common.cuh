@@ -127,7 +127,7 @@ struct WalkState {
     unsigned int slow_count;           // rows the fast kernel handed to the row-group kernel this step
     unsigned int fast_rows;            // rows the fast kernels computed this step
     unsigned int big_rows;             // long rows among them / built this step (the host then queues the big-row kernel)
-    unsigned int pad8;
+    int32_t win_narrow;                // the window set for the next step is narrow enough for a sharded walk's push regions
     unsigned int built_rows;           // structures built this step
     int32_t fb_unhandled;              // sticky: rows were deferred in a step that launched no large-row kernel (host retries)
     // window select (tail.cuh): the epilogues collect the values in [win_lo, win_hi) as percentile candidates
@@ -135,7 +135,7 @@ struct WalkState {
     unsigned long long win_lo, win_hi; // window bounds as order-preserving keys
     unsigned long long win_below;      // values strictly below win_lo (this rank)
     unsigned int win_miss_steps;       // diagnostics: steps whose window missed (full select in the tail kernel)
-    int32_t pad6;
+    int32_t win_missed;                // sharded walk: the window missed, the step was rewound and the walk waits for the host
 };
 
 // Exchange block 0 of a sharded walk: level-0 histogram followed by these extras (all uint64, SUM).

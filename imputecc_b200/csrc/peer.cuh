@@ -16,6 +16,7 @@
 // peers read in finish(t) is next written by gather(t+2).
 #pragma once
 #include "select.cuh"
+#include "tail.cuh"
 
 namespace crwr {
 
@@ -23,7 +24,16 @@ constexpr int kPeerFlags = 16;                                       // max rank
 constexpr int kPeerX = kPeerFlags;                                    // [8 | 4096 | 4096]
 constexpr int kPeerCand0 = kPeerX + kXExtras + 2 * kSelectBins;
 constexpr int kPeerCandWords = kCandHeader + CRWR_SHARD_CAND;
-constexpr int kPeerWords = kPeerCand0 + 2 * kPeerCandWords;
+// Window-select steps (peer_tail_kernel): every rank PUSHES its step counters and window candidates into the block of
+// every peer - one region per (step parity, source rank) - and then raises one flag per peer; the consumer waits for the
+// flags and reads local memory only.
+constexpr int kPushCand = 8192;                                      // candidate keys a rank may push per step
+constexpr int kPushBelow = kXExtras, kPushRaw = kXExtras + 1;       // header: 8 counters, values below the window, raw candidate count
+constexpr int kPushBlock = 12;                                       // ... then a candidate block [count, successor, keys...]
+constexpr int kPushWords = kPushBlock + kCandHeader + kPushCand;
+constexpr int kPeerFlags2 = kPeerCand0 + 2 * kPeerCandWords;         // flags of the push exchange
+constexpr int kPeerPush0 = kPeerFlags2 + kPeerFlags;
+constexpr int kPeerWords = kPeerPush0 + 2 * kPeerFlags * kPushWords;
 
 struct PeerInfo {
     unsigned long long* const* blocks;   // device array [world]: every rank's symmetric block
@@ -78,6 +88,8 @@ __device__ __forceinline__ void peer_barrier(const PeerInfo& p, unsigned long lo
 template <typename T>
 __global__ void __launch_bounds__(1024) peer_scan_kernel(WalkState* st, PeerInfo p, unsigned long long* local_xbuf, int level,
                                                          unsigned long long epoch) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (st->done) return;
     if (level == 1 && st->hist1_ready) return;      // level 1 was already resolved by the level-0 call (prediction hit)
     const int t = threadIdx.x;
@@ -139,6 +151,8 @@ template <typename T>
 __global__ void __launch_bounds__(1024) peer_finish_kernel(FinishArgs a, PeerInfo p, unsigned long long* gathered, int parity,
                                                            unsigned long long epoch) {
     __shared__ __align__(16) unsigned char scratch[kFinishScratchBytes];
+    pdl_wait();
+    pdl_launch_dependents();
     if (a.st->done) return;
     unsigned long long* mine = p.blocks[p.rank];
     // always a barrier: on step 0 it protects the counters a slower peer may still be summing
@@ -163,6 +177,159 @@ __global__ void __launch_bounds__(1024) peer_finish_kernel(FinishArgs a, PeerInf
     // every peer has read this rank's counters and histograms of the step (they signalled the barrier above,
     // or the scan barrier on step 0, only after doing so): clear them for the next step
     for (int i = threadIdx.x; i < kXExtras + 2 * kSelectBins; i += blockDim.x) mine[kPeerX + i] = 0ull;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Settled sharded walk: the percentile cut of a step from ONE cross-GPU synchronisation.  The propagation epilogues
+// of every rank have classified their values against the window [lo, hi) that the previous step derived from its cut
+// (replicated state, identical on all ranks): values below it counted, keys inside it collected, smallest key above
+// it kept.  This kernel (one CTA per rank)
+//   1. pushes [8 step counters | below | candidate count | successor | keys] into its region of every peer's block
+//      (stores over NVLink, coalesced), fences, and raises its flag in every peer's block;
+//   2. waits for the flags of all peers - from here on everything it reads is local memory;
+//   3. sums the counters, concatenates the candidates and - when the order statistics of the percentile lie among
+//      them - selects the cut and runs the finish step, exactly like the unsharded tail (tail.cuh).
+// Integer sums and the union of the candidate sets do not depend on the rank, so every rank derives the same cut and
+// the same stop decision.  A window that misses (or was not set, or overflowed a region) is no error: every rank sees
+// the same miss, rewinds its step counters and stops with `win_missed`; the host then queues this step again the
+// three-barrier way (peer_scan / peer_finish above).
+// Regions alternate by step parity: a rank can only push step t+2 after every peer has raised the flag of step t+1,
+// which a peer does after it has finished reading step t.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) peer_tail_kernel(FinishArgs a, PeerInfo p, unsigned long long* local_xbuf,
+                                                         unsigned long long* my_cand, unsigned long long* next_cand, int parity,
+                                                         unsigned long long epoch) {
+    __shared__ __align__(16) unsigned char scratch[kFinishScratchBytes];
+    __shared__ int s_hit, s_free;
+    const int t = threadIdx.x;
+    pdl_wait();
+    pdl_launch_dependents();
+    WalkState* gst = a.st;
+    WalkState* st = finish_state_ptr(scratch);
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(gst);
+        unsigned* dst = reinterpret_cast<unsigned*>(st);
+        for (int i = t; i < (int)(sizeof(WalkState) / 4); i += blockDim.x) dst[i] = __ldcg(src + i);
+    }
+    __syncthreads();
+    if (st->done) return;
+    unsigned long long* mine = p.blocks[p.rank];
+    // ---- 1. push
+    const unsigned long long raw = my_cand[0];
+    const unsigned long long npush = raw < (unsigned long long)kPushCand ? raw : (unsigned long long)kPushCand;
+    const int reg = kPeerPush0 + (parity * kPeerFlags + p.rank) * kPushWords;
+    unsigned long long hdr = 0ull;
+    switch (t) {
+        case kXSq0: hdr = st->sq_limb[0]; break;
+        case kXSq1: hdr = st->sq_limb[1]; break;
+        case kXSq2: hdr = st->sq_limb[2]; break;
+        case kXNnzIn: hdr = st->nnz_in; break;
+        case kXNnzNew: hdr = st->nnz_exact; break;
+        case kXCapOvf: hdr = (unsigned long long)st->capacity_overflow; break;
+        case kXSelOvf: hdr = (unsigned long long)st->select_overflow; break;
+        case kXFallback: hdr = st->fb_count; break;
+        case kPushBelow: hdr = st->win_below; break;
+        case kPushRaw: hdr = raw; break;
+        case kPushBlock: hdr = npush; break;
+        case kPushBlock + 1: hdr = my_cand[1]; break;
+        default: break;
+    }
+    for (int r = 0; r < p.world; ++r) {
+        unsigned long long* dst = p.blocks[r] + reg;
+        if (t < kPushBlock + kCandHeader) dst[t] = hdr;
+        for (unsigned long long i = t; i < npush; i += blockDim.x) dst[kPushBlock + kCandHeader + i] = my_cand[kCandHeader + i];
+    }
+    __syncthreads();
+    if (t == 0) __threadfence_system();
+    __syncthreads();
+    // ---- 2. one flag per peer, then wait for theirs
+    if (t < p.world) {
+        st_release_sys(p.blocks[t] + kPeerFlags2 + p.rank, epoch);
+        const unsigned long long* flag = mine + kPeerFlags2 + t;
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(flag) < epoch) {
+            if (global_ns() - t0 > 10000000000ull) { st->peer_timeout = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (t == 0) __threadfence_system();
+    __syncthreads();
+    // ---- 3. merge (local memory), decide
+    const unsigned long long* regs = mine + kPeerPush0 + (long long)parity * kPeerFlags * kPushWords;
+    if (t < kXExtras) {
+        unsigned long long sum = 0;
+        for (int r = 0; r < p.world; ++r) sum += regs[(long long)r * kPushWords + t];
+        local_xbuf[t] = sum;
+    }
+    if (t == 0) {
+        unsigned long long below = 0, c = 0, n = 0;
+        int ovf = 0;
+        for (int r = 0; r < p.world; ++r) {
+            const unsigned long long* rg = regs + (long long)r * kPushWords;
+            below += rg[kPushBelow];
+            c += rg[kPushBlock];
+            n += rg[kXNnzNew];
+            if (rg[kPushRaw] > (unsigned long long)kPushCand) ovf = 1;
+        }
+        int hit = 0, free_bits = -1;
+        if (st->win_on && n > 0 && !ovf && !st->peer_timeout) {
+            virtual_index<T>(st, n);
+            const unsigned long long k = st->rank_k;
+            if (below <= k && k < below + c) {
+                hit = 1;
+                st->below = below;
+                st->prefix = 0;
+                st->bin_count = c;
+                const unsigned long long x = st->win_lo ^ (st->win_hi - 1ull);
+                free_bits = x ? 64 - __clzll((long long)x) : 0;
+                if (free_bits < 1) free_bits = 1;
+            }
+        }
+        if (st->peer_timeout) hit = 1;          // the finish step stops the walk with the error
+        s_hit = hit;
+        s_free = free_bits;
+    }
+    __syncthreads();
+    if (s_hit) {
+        a.xch = local_xbuf;
+        a.blocks = const_cast<unsigned long long*>(regs) + kPushBlock;
+        a.n_blocks = p.world;
+        a.block_stride = kPushWords;
+        a.cand_cap = (unsigned long long)kPushCand;
+        a.own_block = next_cand;                // the candidate block of the next step (its last readers are long gone)
+        finish_step_body<T>(a, scratch, s_free, true, true);
+        if (t == 0) { my_cand[0] = 0ull; my_cand[1] = ~0ull; }
+        return;
+    }
+    // ---- a miss: rewind the step (every rank does), stop with win_missed; the host queues the step again
+    if (t == 0) {
+        st->win_miss_steps += 1;
+        st->cursor = 0; st->nnz_exact = 0; st->nnz_in = 0; st->max_row_len = 0; st->max_kept = 0;
+        st->row_counter = 0; st->fb_counter = 0; st->fb_count = 0;
+        st->sq_limb[0] = 0; st->sq_limb[1] = 0; st->sq_limb[2] = 0;
+        st->slow_count = 0; st->fast_rows = 0; st->built_rows = 0; st->win_below = 0;
+        st->tick_dense = 0; st->tick_hist1 = 0; st->tick_gather = 0; st->tick_prop = 0;
+        st->scan_done = 0; st->hist1_ready = 0; st->unordered_rows = 0;
+        st->win_on = 0;
+        st->win_missed = 1;
+        st->done = 1;
+        st->stop_reason = CRWR_STOP_RUNNING;
+        my_cand[0] = 0ull; my_cand[1] = ~0ull;
+    }
+    __syncthreads();
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(st);
+        unsigned* dst = reinterpret_cast<unsigned*>(gst);
+        for (int i = t; i < (int)(sizeof(WalkState) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    // the histograms may hold this attempt's counts (no window was set): clear them for the second attempt
+    for (int i = t; i < kXExtras + 2 * kSelectBins; i += blockDim.x) mine[kPeerX + i] = 0ull;
+}
+
+// After a polled miss: the walk goes on (the host queues the missed step again, histogram select).
+__global__ void peer_redo_kernel(WalkState* st) {
+    if (threadIdx.x == 0 && st->win_missed) { st->win_missed = 0; st->done = 0; }
 }
 
 }  // namespace crwr

@@ -191,6 +191,7 @@ struct FinishArgs {
     int32_t next_win;                     // 1: derive a select window for the next step from this step's cut (tail.cuh)
     int32_t dense_launched;               // 0: the step launched no large-row kernel, deferred rows are an error (host retries)
     float win_scale, win_min, win_max, win_rel_max;   // window half-width = clamp(win_scale x |relative move of the cut|, win_min, win_max)
+    long long win_narrow_cands;           // sharded walk: candidates the ranks' push regions take together (with a margin)
 };
 
 // Shared-memory scratch the finish step needs (carved from the caller's buffer, 16-byte aligned).
@@ -360,7 +361,7 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
         if (fb > 0 && !a.dense_launched) st->fb_unhandled = 1;
         // select window of the next step: the cut moves less and less, so it will lie within a few times its last move
         {
-            int on = 0;
+            int on = 0, narrow = 0;
             if (a.next_win && cut_applied && st->cut_on && st->cut > 0.0) {
                 const double c0 = st->cut, c1 = cut;
                 const double rel = fabs(c1 - c0) / c1;
@@ -369,11 +370,15 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
                 const T lo = (T)(c1 * (1.0 - dl)), hi = (T)(c1 * (1.0 + dl));
                 if (rel <= (double)a.win_rel_max && lo > (T)0 && hi > lo) {
                     on = 1;
+                    // sharded walk: about 0.4 x dl of the values fall into the window (measured on the synthetic workloads,
+                    // whose value density at the cut is ~0.2 per unit of log value); they must fit the ranks' push regions
+                    narrow = 0.4 * dl * (double)nnz_new <= (double)a.win_narrow_cands ? 1 : 0;
                     st->win_lo = (unsigned long long)KO::enc(lo);
                     st->win_hi = (unsigned long long)KO::enc(hi);
                 }
             }
             st->win_on = on;
+            st->win_narrow = narrow;
         }
         // rows written in slot-claim order (row-group kernel) are only valid operands behind a cut
         if (st->unordered_rows && a.do_select && !cut_applied && st->n_total > 0 && !st->capacity_overflow && !st->select_overflow)

@@ -212,9 +212,35 @@ def _peer_topology_ok(dist, group, device) -> bool:
     return all(d == me or torch.cuda.can_device_access_peer(me, d) for _, d in names)
 
 
+def enqueue_peer_step(walker, issued):
+    """One step of a peer-attached shard on the walker's stream: the window form (one cross-GPU synchronisation) once
+    the walk has settled, else the three-barrier form."""
+    lib, h = walker.lib, walker.handle
+    st = walker._stream()
+    if lib.crwr_step_window(h):
+        _lib.check(lib.crwr_step_propagate(h, st))
+        _lib.check(lib.crwr_step_peer_tail(h, st))
+        return
+    _lib.check(lib.crwr_step_propagate(h, st))
+    if issued >= 1:
+        _lib.check(lib.crwr_step_peer_scan(h, 0, st))
+        _lib.check(lib.crwr_step_hist(h, 1, st))
+        _lib.check(lib.crwr_step_peer_scan(h, 1, st))
+        _lib.check(lib.crwr_step_gather(h, st))
+    else:
+        _lib.check(lib.crwr_step_peer_scan(h, -1, st))
+    _lib.check(lib.crwr_step_peer_finish(h, st))
+
+
+WINDOW_MISSED = 4       # crwr_status.capacity_overflow bit: the select window of a sharded step missed
+
+
 def run_sharded_walk_peer(walker, perc, max_steps):
     """The sharded walk with the exchanges fused into the consumer kernels (peer.cuh): no collective call in
-    the step loop, only kernel launches on this rank's stream.  The walker must be peer-attached."""
+    the step loop, only kernel launches on this rank's stream.  The walker must be peer-attached.
+
+    Every rank sees the same window miss in the same step (the merged data are identical), so the ranks repeat that
+    step in lockstep without talking to each other."""
     from .crwr import next_row_hints, poll_chunk
     lib, h = walker.lib, walker.handle
     issued = 0
@@ -222,19 +248,13 @@ def run_sharded_walk_peer(walker, perc, max_steps):
     while True:
         chunk = min(poll_chunk(issued), max_steps - issued)
         walker.set_row_hints(*hints)
-        for _ in range(chunk):
-            st = walker._stream()
-            _lib.check(lib.crwr_step_propagate(h, st))
-            if issued >= 1:
-                _lib.check(lib.crwr_step_peer_scan(h, 0, st))
-                _lib.check(lib.crwr_step_hist(h, 1, st))
-                _lib.check(lib.crwr_step_peer_scan(h, 1, st))
-                _lib.check(lib.crwr_step_gather(h, st))
-            else:
-                _lib.check(lib.crwr_step_peer_scan(h, -1, st))
-            _lib.check(lib.crwr_step_peer_finish(h, st))
-            issued += 1
+        _lib.check(lib.crwr_walk_enqueue_peer(h, chunk, walker._stream()))
+        issued += chunk
         status = walker.poll()
+        if int(status.capacity_overflow) & WINDOW_MISSED:
+            _lib.check(lib.crwr_walk_redo(h, walker._stream()))
+            issued = int(status.steps_done)          # the steps queued behind the miss were skipped
+            continue
         if status.stop_reason != 0 or issued >= max_steps:
             return status
         hints = walker.row_hints(status, perc, issued)      # local statistics: sizing affects speed only

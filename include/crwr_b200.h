@@ -84,7 +84,8 @@ typedef struct crwr_step_record {
 typedef struct crwr_status {
     int32_t steps_done;
     int32_t stop_reason;        /* CRWR_STOP_* */
-    int32_t capacity_overflow;  /* 1 = an iterate buffer overflowed; results invalid */
+    int32_t capacity_overflow;  /* bit 0: an iterate buffer overflowed, bit 1: candidate buffer overflowed (results invalid);
+                                 * bit 2: sharded walk only - the select window missed, call crwr_walk_redo */
     int32_t fallback_rows;      /* rows that took the large-row path in the last step */
     int64_t nnz_iterate;        /* entries currently stored (before the last cut) */
     int64_t max_row_len;        /* longest stored row */
@@ -167,6 +168,19 @@ int64_t crwr_peer_block_bytes(void);
 int32_t crwr_peer_attach(crwr_handle h, void* d_block_ptrs, int32_t rank, uint64_t epoch_base);
 int32_t crwr_step_peer_scan(crwr_handle h, int32_t level, void* stream);
 int32_t crwr_step_peer_finish(crwr_handle h, void* stream);
+/* Once the walk has settled (the cut moves by a few percent per step) a sharded step needs ONE cross-GPU
+ * synchronisation: the propagation classifies its values against a window around the expected cut (replicated state),
+ * and crwr_step_peer_tail pushes [step counters | values below the window | the keys inside it] into every peer's
+ * block, raises one flag per peer, waits for theirs, and derives the cut and the stop decision from local memory:
+ *   if (crwr_step_window(h)) { crwr_step_propagate; crwr_step_peer_tail; } else { ...the sequence above... }
+ * A window that misses is no error: every rank rewinds the step and stops; crwr_walk_poll then reports bit 2 of
+ * crwr_status.capacity_overflow, and after crwr_walk_redo the missed step is queued again the three-barrier way
+ * (crwr_step_window answers 0 for it).  Replaces the exchange part of utility.py:283-304 on several GPUs. */
+int32_t crwr_step_window(crwr_handle h);
+int32_t crwr_step_peer_tail(crwr_handle h, void* stream);
+int32_t crwr_walk_redo(crwr_handle h, void* stream);
+/* n_steps whole steps of a peer-attached shard (either form, as crwr_step_window decides) in one call. */
+int32_t crwr_walk_enqueue_peer(crwr_handle h, int32_t n_steps, void* stream);
 
 /* Synchronises the stream and fills *h_out. */
 int32_t crwr_walk_poll(crwr_handle h, crwr_status* h_out, void* stream);

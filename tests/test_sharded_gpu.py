@@ -85,3 +85,4 @@ def test_sharded_walk_equals_unsharded(cuda_device, shards, dtype):
                [(t["nnz_in"], t["nnz_new"], t["cut"], t["delta"]) for t in trace1[1:]]
     got.sort_indices(); want.sort_indices()
     assert same_support(got, want) and np.array_equal(got.data, want.data)   # bit-identical, any sharding
+

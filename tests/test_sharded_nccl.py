@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, env):
     import sys
     sys.path.insert(0, REPO)
     import torch.distributed as dist
@@ -29,6 +29,7 @@ def _worker(rank, world, port, out_dir):
     from imputecc_b200 import synth
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ.update(env)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     M, idx = synth.make_workload(synth.Workload("n", 6000, 960, 100, 16))
@@ -41,13 +42,17 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_gpu_nccl_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("env", [{},                                                       # peer path: window steps (one sync per step)
+                                 {"CRWR_WIN_MIN": "1e-7", "CRWR_WIN_SCALE": "0.01"},      # windows that miss: steps repeated in lockstep
+                                 {"CRWR_WIN_STEP": "0"},                                   # three flag barriers per step
+                                 {"CRWR_SHARDED_EXCHANGE": "nccl"}])                       # NCCL collectives
+def test_two_gpu_nccl_matches_single_gpu(tmp_path, env):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
     import imputecc_b200 as pkg
     from imputecc_b200 import synth
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), env), nprocs=2, join=True)
     M, idx = synth.make_workload(synth.Workload("n", 6000, 960, 100, 16))
     for name, dtype in (("f32", np.float32), ("f64", np.float64)):
         want, info = pkg.crwr_impute(M, idx, 0.5, 80, dtype=dtype, device="cuda:0", return_info=True)
