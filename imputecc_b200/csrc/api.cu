@@ -721,7 +721,8 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, bool win_step, cu
     // the large-row kernel: always behind a histogram-select step (its last CTA scans the histograms); behind a
     // window-select step only when this walk has deferred rows before (a deferral it then misses is caught by the finish
     // step and the host retries with the kernel always queued)
-    h->dense_launched = !win_step || h->dense_always || h->fb_seen;
+    // (a sharded histogram step needs no scan tail either: same rule as a window step)
+    h->dense_launched = (!win_step && (fused || h->cfg.n_shards == 1)) || h->dense_always || h->fb_seen;
     if (h->dense_launched) {
         a.row_order = nullptr;
         a.row_list_count = nullptr;
@@ -1367,6 +1368,7 @@ int32_t crwr_step_hist(crwr_handle h, int32_t level, void* stream) {
     if (level == 0 && h->hist0_fused) return CRWR_OK;        // filled by the propagate epilogue
     int e = f64 ? launch_hist<double>(h, parity ^ 1, level, 0, st) : launch_hist<float>(h, parity ^ 1, level, 0, st);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "hist launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    tl_mark(h, st, "hist pass");
     return CRWR_OK;
 }
 int32_t crwr_step_scan(crwr_handle h, int32_t level, void* stream) {
@@ -1380,6 +1382,7 @@ int32_t crwr_step_gather(crwr_handle h, void* stream) {
     STEP_PROLOGUE();
     int e = f64 ? launch_gather<double>(h, parity ^ 1, 0, st) : launch_gather<float>(h, parity ^ 1, 0, st);
     if (e) CRWR_FAIL(CRWR_ERR_CUDA, "gather launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    tl_mark(h, st, "gather");
     return CRWR_OK;
 }
 int32_t crwr_step_finish(crwr_handle h, const void* d_gathered_blocks, void* stream) {
@@ -1424,6 +1427,7 @@ int32_t crwr_step_peer_scan(crwr_handle h, int32_t level, void* stream) {
     if (f64) launch_k(use_pdl(h), peer_scan_kernel<double>, 1, 1024, 0, st, h->at<WalkState>(h->L.state), h->peer, local, level, epoch);
     else launch_k(use_pdl(h), peer_scan_kernel<float>, 1, 1024, 0, st, h->at<WalkState>(h->L.state), h->peer, local, level, epoch);
     LAUNCH_CHECK();
+    tl_mark(h, st, level == 1 ? "peer scan 1" : "peer scan 0");
     return CRWR_OK;
 }
 
@@ -1439,6 +1443,7 @@ int32_t crwr_step_peer_finish(crwr_handle h, void* stream) {
     if (f64) launch_k(use_pdl(h), peer_finish_kernel<double>, 1, 1024, 0, st, a, h->peer, gathered, step & 1, epoch);
     else launch_k(use_pdl(h), peer_finish_kernel<float>, 1, 1024, 0, st, a, h->peer, gathered, step & 1, epoch);
     LAUNCH_CHECK();
+    tl_mark(h, st, "peer finish");
     h->steps_enqueued += 1;
     h->redo_hist = false;
     return CRWR_OK;
@@ -1457,6 +1462,7 @@ int32_t crwr_step_peer_tail(crwr_handle h, void* stream) {
     if (f64) launch_k(use_pdl(h), peer_tail_kernel<double>, 1, 1024, 0, st, a, h->peer, local, cand_ptr(h, step), cand_ptr(h, step + 1), step & 1, epoch);
     else launch_k(use_pdl(h), peer_tail_kernel<float>, 1, 1024, 0, st, a, h->peer, local, cand_ptr(h, step), cand_ptr(h, step + 1), step & 1, epoch);
     LAUNCH_CHECK();
+    tl_mark(h, st, "peer tail");
     h->steps_enqueued += 1;
     return CRWR_OK;
 }

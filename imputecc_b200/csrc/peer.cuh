@@ -54,6 +54,35 @@ __device__ __forceinline__ unsigned long long ld_peer(const unsigned long long* 
     return v;
 }
 
+// Sum over the ranks of word `idx` of every rank's block region `off`, for up to four words per thread at once: the
+// remote loads of a batch (four ranks x four words) are all issued before the first of them is consumed - one
+// dependent NVLink round trip per load was most of the exchange time.
+__device__ __forceinline__ void peer_sum4(const PeerInfo& p, int off, const int idx[4], int n, unsigned long long out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0ull;
+    for (int r0 = 0; r0 < p.world; r0 += 4) {
+        unsigned long long v[4][4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const unsigned long long* base = p.blocks[r0 + rr < p.world ? r0 + rr : p.rank] + off;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[rr][k] = (r0 + rr < p.world && k < n) ? ld_peer(base + idx[k]) : 0ull;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[k] += v[rr][k];
+    }
+}
+// All kSelectBins words of region `off`, summed over the ranks, into dst (1024 threads, four words each).
+__device__ __forceinline__ void peer_sum_bins(const PeerInfo& p, int off, unsigned long long* dst) {
+    const int t = threadIdx.x;
+    const int idx[4] = {t, t + 1024, t + 2048, t + 3072};
+    unsigned long long s4[4];
+    peer_sum4(p, off, idx, 4, s4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[idx[k]] = s4[k];
+}
+
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -115,12 +144,8 @@ __global__ void __launch_bounds__(1024) peer_scan_kernel(WalkState* st, PeerInfo
     }
     if (level < 0) return;
     {
-        const int off = kPeerX + kXExtras + level * kSelectBins;
-        for (int b = t; b < kSelectBins; b += 1024) {
-            unsigned long long s = 0;
-            for (int r = 0; r < p.world; ++r) s += ld_peer(p.blocks[r] + off + b);
-            local_xbuf[kXExtras + level * kSelectBins + b] = s;
-        }
+        static_assert(kSelectBins == 4096, "peer_sum_bins covers 4096 bins with 1024 threads");
+        peer_sum_bins(p, kPeerX + kXExtras + level * kSelectBins, local_xbuf + kXExtras + level * kSelectBins);
         __syncthreads();
         scan_level<T, 1024>(st, local_xbuf + kXExtras, level);
     }
@@ -131,12 +156,7 @@ __global__ void __launch_bounds__(1024) peer_scan_kernel(WalkState* st, PeerInfo
         const bool hit = st->pred_valid && st->prefix == st->pred_prefix0;
         __syncthreads();
         if (hit) {
-            const int off = kPeerX + kXExtras + kSelectBins;
-            for (int b = t; b < kSelectBins; b += 1024) {
-                unsigned long long s = 0;
-                for (int r = 0; r < p.world; ++r) s += ld_peer(p.blocks[r] + off + b);
-                local_xbuf[kXExtras + kSelectBins + b] = s;
-            }
+            peer_sum_bins(p, kPeerX + kXExtras + kSelectBins, local_xbuf + kXExtras + kSelectBins);
             __syncthreads();
             scan_level<T, 1024>(st, local_xbuf + kXExtras, 1);
             if (t == 0) st->hist1_ready = 1;

@@ -20,6 +20,8 @@ w.build_transition(M.indptr, M.indices, M.data, pkg.markers_first_order(n, idx))
 peer = sharded.PeerExchange.get(dist, dist.group.WORLD, dev)
 lib, h = w.lib, w.handle
 for rep in range(3):
+    if rank == 0 and os.environ.get("CRWR_TIMELINE"):
+        lib.crwr_profile(h, 1)
     peer.attach(w)
     w.walk_init(0.5, 80)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -45,6 +47,9 @@ for rep in range(3):
             break
         hints = w.row_hints(st, 80, issued)
     wall = (time.perf_counter() - t_all) * 1e3
+    if rank == 0 and os.environ.get("CRWR_TIMELINE"):
+        ms, nl = _lib.C.c_double(0), _lib.C.c_int64(0)
+        lib.crwr_profile_read(h, _lib.C.byref(ms), _lib.C.byref(nl), w._stream())
     if rank == 0:
         print("rep %d: %d steps, wall %.3f ms, misses %d | chunks (steps, window form, us per step): %s" % (
             rep, st.steps_done, wall, misses, " ".join("%d/%d/%.0f" % c for c in log)), flush=True)
