@@ -63,6 +63,7 @@ _SIGNATURES = {
     "crwr_get_group_shape": (C.c_int32, [_P, C.POINTER(C.c_int64)]),
     "crwr_profile": (C.c_int32, [_P, C.c_int32]),
     "crwr_profile_phases": (C.c_int32, [_P, C.POINTER(C.c_double)]),
+    "crwr_profile_steps": (C.c_int32, [_P, C.POINTER(C.c_double), C.c_int32]),
     "crwr_profile_read": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _P]),
     "crwr_walk_enqueue": (C.c_int32, [_P, C.c_int32, _P]),
     "crwr_step_propagate": (C.c_int32, [_P, _P]),

@@ -260,6 +260,7 @@ struct crwr_handle_s {
     std::vector<cudaEvent_t> marks;             // profile mode: step start + one event after each kernel of the step
     std::vector<int> mark_ids;
     double phase_ms[4] = {0, 0, 0, 0};
+    std::vector<double> pair_ms;                // durations of the propagation launches of the last profiled walk, step by step
     bool timeline = false;                      // CRWR_TIMELINE=1 (developer aid): an event after every kernel of a profiled walk,
     std::vector<std::pair<cudaEvent_t, const char*>> tl;   // durations printed to stderr by crwr_profile_read
     template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
@@ -346,10 +347,12 @@ int configure_struct_shape(crwr_handle_s* h, long long max_row_len, long long ma
     const long long n = h->cfg.n_contigs;
     const long long rows = h->cfg.row_end - h->cfg.row_begin;
     const size_t win_bytes = kHistWin * sizeof(unsigned int);
-    long long no = round_up(max_row_len + max_row_len * 3 / 10 + 32, 32);
+    // (a structure covers what the superset K+ reaches, more than the stored row the hint was taken from)
+    long long no = round_up(max_row_len + max_row_len * 6 / 10 + 32, 32);
     if (no < 128) no = 128;
     if (no > n + 1) no = round_up(n + 1, 32);
-    long long km = round_up(max_kept + max_kept * 3 / 10 + 16, 32);
+    // (K+ holds the entries above alpha x cut: up to about twice the kept ones the hint counts)
+    long long km = round_up(max_kept * 22 / 10 + 16, 32);
     if (km < 64) km = 64;
     if (km > no) km = no;
     SymShape sh;
@@ -1242,9 +1245,10 @@ int32_t crwr_profile_read(crwr_handle h, double* h_total_ms, int64_t* h_launches
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     double total = 0.0;
     long long n = 0;
+    h->pair_ms.clear();
     for (size_t i = 0; i + 1 < h->ev.size(); i += 2) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) { total += ms; ++n; }
+        if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) { total += ms; ++n; h->pair_ms.push_back((double)ms); }
         cudaEventDestroy(h->ev[i]);
         cudaEventDestroy(h->ev[i + 1]);
     }
@@ -1273,6 +1277,13 @@ int32_t crwr_profile_read(crwr_handle h, double* h_total_ms, int64_t* h_launches
     h->mark_ids.clear();
     h->phase_ms[1] = phase[1]; h->phase_ms[2] = phase[2]; h->phase_ms[3] = phase[3];
     return CRWR_OK;
+}
+
+int32_t crwr_profile_steps(crwr_handle h, double* h_ms, int32_t cap) {
+    if (!h || !h_ms || cap < 0) CRWR_FAIL(CRWR_ERR_INVALID, "bad argument");
+    const int32_t n = (int32_t)h->pair_ms.size() < cap ? (int32_t)h->pair_ms.size() : cap;
+    for (int32_t i = 0; i < n; ++i) h_ms[i] = h->pair_ms[i];
+    return n;
 }
 
 int32_t crwr_profile_phases(crwr_handle h, double* h_ms3) {

@@ -227,6 +227,9 @@ int32_t crwr_profile(crwr_handle h, int32_t enable);
 int32_t crwr_profile_read(crwr_handle h, double* h_total_ms, int64_t* h_launches, void* stream);
 /* After crwr_profile_read: summed durations (ms) of the step phases since the previous read:
  * [0] propagate + large-row kernel, [1] level-1 histogram pass, [2] candidate gather + finish. */
+/* Per walk step of the last profiled walk: milliseconds of its propagation launches (what crwr_profile_read sums up).
+ * Returns the number of entries written (at most cap). */
+int32_t crwr_profile_steps(crwr_handle h, double* h_ms, int32_t cap);
 int32_t crwr_profile_phases(crwr_handle h, double* h_ms3);
 
 /* Launch counter: kernels this library launched since the last reset (bench gpu_launches). */
