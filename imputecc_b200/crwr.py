@@ -566,28 +566,39 @@ def crwr_impute(normcc, marker_idx_sorted, rp, perc, tol: float = DEFAULT_TOL, m
     return (E, info) if return_info else E
 
 
-def imputation_b200(self, dtype=np.float32, device=None):
+def imputation_b200(self, dtype=np.float32, device=None, hand_off: str = "lil"):
     """Replacement for ``ImputeMatrix._imputation`` (imputation.py:93-129): same attributes read
     (normcc_matrix, contig_markers, dict_contigRev, contig_info, rwr_rp, rwr_perc), same tuple
-    returned: (contig_local, dict_contigRevLocal, imputed lil_matrix)."""
+    returned: (contig_local, dict_contigRevLocal, imputed lil_matrix).
+
+    ``hand_off="csr"`` returns the imputed matrix as a CSR matrix instead: every consumer only calls ``.tocoo()``,
+    ``.tolil()`` and ``.copy().tocsr()`` on it, and the LIL conversion alone costs ten times the imputation
+    (imputecc_b200/handoff.py)."""
+    if hand_off not in ("lil", "csr"):
+        raise ValueError("hand_off must be 'lil' or 'csr'")
     names = list(self.contig_markers.keys())
     idx = np.sort(np.array([self.dict_contigRev[c] for c in names], dtype=np.int64))     # :101
     contig_local = self.contig_info[idx, :]                                             # :102
     rev_local = {name: i for i, name in enumerate(contig_local[:, 0])}                  # :104-106
     E = crwr_impute(self.normcc_matrix, idx, self.rwr_rp, self.rwr_perc, DEFAULT_TOL, DEFAULT_MAX_STEPS,
                     dtype=dtype, device=device)
-    return contig_local, rev_local, E.tolil()                                           # :129
+    return contig_local, rev_local, (E.tolil() if hand_off == "lil" else E)            # :129
 
 
-def install(imputation_module, mode: str = "outer"):
+def install(imputation_module, mode: str = "outer", hand_off: str = "lil"):
     """Rebind the reference's entry point to the GPU path.
 
     ``imputation_module`` is the imported ``Script.imputation``.  mode "outer" replaces
     ``ImputeMatrix._imputation``; mode "inner" rebinds the name ``random_walk_cpu`` that
     ``Script.imputation`` imported (imputation.py:9), leaving pre/post-processing to scipy.
     """
+    if hand_off not in ("lil", "csr"):
+        raise ValueError("hand_off must be 'lil' or 'csr'")
     if mode == "outer":
-        imputation_module.ImputeMatrix._imputation = imputation_b200
+        if hand_off == "lil":
+            imputation_module.ImputeMatrix._imputation = imputation_b200
+        else:
+            imputation_module.ImputeMatrix._imputation = lambda self: imputation_b200(self, hand_off="csr")
     elif mode == "inner":
         imputation_module.random_walk_cpu = random_walk_b200
     else:

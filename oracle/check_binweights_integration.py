@@ -28,7 +28,7 @@ from imputecc_b200 import synth                                 # noqa: E402
 from imputecc_b200.binning import bins_to_arrays                # noqa: E402
 from oracle import binweights_oracle as bw                      # noqa: E402
 from oracle import crwr_oracle as oracle                        # noqa: E402
-from oracle.make_golden_binweights import planted_markers, smg_iterations   # noqa: E402
+from oracle.match_inputs import planted_markers, smg_iterations   # noqa: E402
 
 SNIPPET = '''
 bin_ptr, members = bins_to_arrays(bins, dict_contigRev)

@@ -25,40 +25,7 @@ for name in ("igraph", "leidenalg", "Bio", "Bio.SeqIO"):     # imported at modul
 from Script import utility as ref_utility          # noqa: E402  (needs PYTHONPATH=/root/reference)
 from imputecc_b200 import synth                    # noqa: E402
 from oracle import crwr_oracle as oracle           # noqa: E402
-
-
-def planted_markers(wl, idx, rng):
-    """Each marker contig carries 1-3 of 107 single-copy genes, no gene twice inside a planted genome
-    (SURVEY.md §8d config 5)."""
-    n = wl.n_contigs
-    g = n // wl.genome_size
-    lab = np.sort(np.random.default_rng(wl.matrix_seed).integers(0, g, n))      # the generator's genome labels
-    used = {}
-    contig_markers = {}
-    for i in idx:
-        k = int(rng.integers(1, 4))
-        free = [x for x in range(107) if x not in used.setdefault(int(lab[i]), set())]
-        genes = [int(x) for x in rng.choice(free, size=min(k, len(free)), replace=False)]
-        used[int(lab[i])].update(genes)
-        contig_markers["contig%05d" % i] = ["gene%03d" % x for x in genes]
-    return contig_markers
-
-
-def smg_iterations(contig_markers):
-    """The iteration order PreCluster derives (pre_clustering.py:11-44): genes by contig count, ties by the total
-    number of genes on their contigs - restated for input generation only."""
-    marker_contigs = {}
-    for c, genes in contig_markers.items():
-        for gname in genes:
-            marker_contigs.setdefault(gname, []).append(c)
-    counts = {gname: len(cs) for gname, cs in marker_contigs.items()}
-    out, n = {}, 0
-    for cnt in sorted(set(counts.values()), reverse=True):
-        tot = {gname: sum(len(contig_markers[c]) for c in marker_contigs[gname]) for gname in counts if counts[gname] == cnt}
-        for gname, _ in sorted(tot.items(), key=lambda kv: kv[1], reverse=True):
-            out[n] = marker_contigs[gname]
-            n += 1
-    return out
+from oracle.match_inputs import planted_markers, smg_iterations   # noqa: E402,F401
 
 
 def trace_match_contigs(smg_iteration, contig_markers, lil, rev, w_intra, w_inter):

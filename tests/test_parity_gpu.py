@@ -399,6 +399,17 @@ def test_install_rebinds_the_reference_entry_points(cuda_device, mode):
     assert _bit_equal(imp.imputed_matrix.tocsr(), load_csr(rec, "E32"))
     with pytest.raises(ValueError):
         pkg.install(mod, "sideways")
+    if mode == "outer":
+        # the CSR hand-off (imputecc_b200/handoff.py): the same matrix without the LIL conversion, and every call the
+        # clustering stages make on it still works
+        mod2 = _stub_imputation_module()
+        pkg.install(mod2, "outer", hand_off="csr")
+        imp2 = mod2.ImputeMatrix(normcc, info, markers, 0.5, 80)
+        assert sp.isspmatrix_csr(imp2.imputed_matrix) and _bit_equal(imp2.imputed_matrix, load_csr(rec, "E32"))
+        assert np.array_equal(np.sort(imp2.imputed_matrix.tocoo().data), np.sort(imp.imputed_matrix.tocoo().data))
+        assert _bit_equal(imp2.imputed_matrix.tolil().tocsr(), imp.imputed_matrix.tocsr())
+        assert _bit_equal(imp2.imputed_matrix.copy().tocsr()[[0, 3, 5], :], imp.imputed_matrix.copy().tocsr()[[0, 3, 5], :])
+        assert pkg.storage_offenders(imp2) == [] and pkg.storage_offenders(imp) == []
 
 
 # ---------------------------------------------------------------------------------------------
