@@ -237,6 +237,7 @@ struct crwr_handle_s {
     bool structs_active = false;                // this walk's decision, taken when the first structure step is queued
     bool redo_hist = false;                     // sharded walk: the next step repeats one whose window missed (histogram select)
     int win_step = 6;                           // first walk step whose cut comes from the window select (CRWR_WIN_STEP; 0: never)
+    bool scan_push = true;                      // sharded histogram steps exchange level 0 (+1) by pushing (CRWR_SCAN_PUSH=0: pull)
     bool sharded_window_ok = false;             // sharded walk: the last poll saw a window narrow enough for the push regions
     int win_step_sharded = 9;
     float alpha = 0.5f;                         // K+ = entries above alpha x cut (CRWR_STRUCT_ALPHA)
@@ -1027,6 +1028,7 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     h->win_step = env_int("CRWR_WIN_STEP", 6);
     if (h->win_step > 0 && h->win_step < 2) h->win_step = 2;
     h->win_step_sharded = env_int("CRWR_WIN_STEP_SHARDED", 9);
+    h->scan_push = env_int("CRWR_SCAN_PUSH", 1) != 0;
 
     if (h->prop_kind != 1) h->win_step = 0;         // the warp-per-row kernel only knows the histogram select
     h->alpha = (float)env_double("CRWR_STRUCT_ALPHA", 0.5);
@@ -1435,7 +1437,12 @@ int32_t crwr_step_peer_scan(crwr_handle h, int32_t level, void* stream) {
     if (level < -1 || level >= kSelectLevels) CRWR_FAIL(CRWR_ERR_INVALID, "level out of range");
     const unsigned long long epoch = h->peer_epoch_base + 3ull * (unsigned long long)h->steps_enqueued + (level == 1 ? 2ull : 1ull);
     unsigned long long* local = h->at<unsigned long long>(h->L.xbuf);
-    if (f64) launch_k(use_pdl(h), peer_scan_kernel<double>, 1, 1024, 0, st, h->at<WalkState>(h->L.state), h->peer, local, level, epoch);
+    if (level == 0 && h->scan_push) {
+        // push form (flags of its own, one epoch per step)
+        const unsigned long long ep = h->peer_epoch_base + (unsigned long long)h->steps_enqueued + 1ull;
+        if (f64) launch_k(use_pdl(h), peer_scan_push_kernel<double>, 1, 1024, 0, st, h->at<WalkState>(h->L.state), h->peer, local, h->steps_enqueued & 1, ep);
+        else launch_k(use_pdl(h), peer_scan_push_kernel<float>, 1, 1024, 0, st, h->at<WalkState>(h->L.state), h->peer, local, h->steps_enqueued & 1, ep);
+    } else if (f64) launch_k(use_pdl(h), peer_scan_kernel<double>, 1, 1024, 0, st, h->at<WalkState>(h->L.state), h->peer, local, level, epoch);
     else launch_k(use_pdl(h), peer_scan_kernel<float>, 1, 1024, 0, st, h->at<WalkState>(h->L.state), h->peer, local, level, epoch);
     LAUNCH_CHECK();
     tl_mark(h, st, level == 1 ? "peer scan 1" : "peer scan 0");

@@ -33,7 +33,11 @@ constexpr int kPushBlock = 12;                                       // ... then
 constexpr int kPushWords = kPushBlock + kCandHeader + kPushCand;
 constexpr int kPeerFlags2 = kPeerCand0 + 2 * kPeerCandWords;         // flags of the push exchange
 constexpr int kPeerPush0 = kPeerFlags2 + kPeerFlags;
-constexpr int kPeerWords = kPeerPush0 + 2 * kPeerFlags * kPushWords;
+// Histogram steps (peer_scan_push_kernel): [8 counters | level-0 histogram | level-1 histogram] pushed the same way.
+constexpr int kHPushWords = kXExtras + 2 * kSelectBins;
+constexpr int kPeerFlags3 = kPeerPush0 + 2 * kPeerFlags * kPushWords;
+constexpr int kPeerHPush0 = kPeerFlags3 + kPeerFlags;
+constexpr int kPeerWords = kPeerHPush0 + 2 * kPeerFlags * kHPushWords;
 
 struct PeerInfo {
     unsigned long long* const* blocks;   // device array [world]: every rank's symmetric block
@@ -164,6 +168,86 @@ __global__ void __launch_bounds__(1024) peer_scan_kernel(WalkState* st, PeerInfo
             for (int b = t; b < kSelectBins; b += 1024) mine[kPeerX + kXExtras + kSelectBins + b] = 0ull;
             if (t == 0) st->hist1_ready = 0;
         }
+    }
+}
+
+// Level 0 of a histogram step, push form: every rank copies [8 counters | level-0 histogram | level-1 histogram
+// pre-filled for the predicted bin] from its own block into its region of every peer's block (64 KB per peer, coalesced
+// stores over NVLink), raises one flag per peer, waits for theirs and sums LOCAL memory - instead of pulling 2 x 4096
+// bins from every peer with dependent remote loads behind two barriers.  When the level-0 bin predicted from the
+// previous cut is the right one (it is, once the cut moves by a few percent), level 1 is resolved here as well and the
+// level-1 pass with its exchange is skipped: two synchronisations per step (this one and the finish) instead of three.
+template <typename T>
+__global__ void __launch_bounds__(1024) peer_scan_push_kernel(WalkState* st, PeerInfo p, unsigned long long* local_xbuf, int parity,
+                                                              unsigned long long epoch) {
+    pdl_wait();
+    pdl_launch_dependents();
+    if (st->done) return;
+    const int t = threadIdx.x;
+    unsigned long long* mine = p.blocks[p.rank];
+    if (t == 0) {
+        unsigned long long* extras = mine + kPeerX;
+        extras[kXSq0] = st->sq_limb[0];
+        extras[kXSq1] = st->sq_limb[1];
+        extras[kXSq2] = st->sq_limb[2];
+        extras[kXNnzIn] = st->nnz_in;
+        extras[kXNnzNew] = st->nnz_exact;
+        extras[kXCapOvf] = (unsigned long long)st->capacity_overflow;
+        extras[kXSelOvf] = (unsigned long long)st->select_overflow;
+        extras[kXFallback] = st->fb_count;
+    }
+    __syncthreads();
+    // ---- push
+    const int reg = kPeerHPush0 + (parity * kPeerFlags + p.rank) * kHPushWords;
+    for (int i0 = 0; i0 < kHPushWords; i0 += 4 * 1024) {
+        unsigned long long v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int i = i0 + k * 1024 + t; v[k] = i < kHPushWords ? mine[kPeerX + i] : 0ull; }
+        for (int r = 0; r < p.world; ++r) {
+            unsigned long long* dst = p.blocks[r] + reg;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int i = i0 + k * 1024 + t; if (i < kHPushWords) dst[i] = v[k]; }
+        }
+    }
+    __syncthreads();
+    if (t == 0) __threadfence_system();
+    __syncthreads();
+    if (t < p.world) {
+        st_release_sys(p.blocks[t] + kPeerFlags3 + p.rank, epoch);
+        const unsigned long long* flag = mine + kPeerFlags3 + t;
+        const unsigned long long limit = st->step <= 1 ? 120000000000ull : 10000000000ull;
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(flag) < epoch) {
+            if (global_ns() - t0 > limit) { st->peer_timeout = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (t == 0) __threadfence_system();
+    __syncthreads();
+    if (st->peer_timeout) return;
+    // ---- sum local memory
+    const unsigned long long* regs = mine + kPeerHPush0 + (long long)parity * kPeerFlags * kHPushWords;
+    for (int i = t; i < kXExtras + kSelectBins; i += 1024) {
+        unsigned long long sum = 0;
+        for (int r = 0; r < p.world; ++r) sum += regs[(long long)r * kHPushWords + i];
+        local_xbuf[i] = sum;
+    }
+    __syncthreads();
+    scan_level<T, 1024>(st, local_xbuf + kXExtras, 0);
+    const bool hit = st->pred_valid && st->prefix == st->pred_prefix0;
+    __syncthreads();
+    if (hit) {
+        for (int i = kXExtras + kSelectBins + t; i < kHPushWords; i += 1024) {
+            unsigned long long sum = 0;
+            for (int r = 0; r < p.world; ++r) sum += regs[(long long)r * kHPushWords + i];
+            local_xbuf[i] = sum;
+        }
+        __syncthreads();
+        scan_level<T, 1024>(st, local_xbuf + kXExtras, 1);
+        if (t == 0) st->hist1_ready = 1;
+    } else {
+        for (int b = t; b < kSelectBins; b += 1024) mine[kPeerX + kXExtras + kSelectBins + b] = 0ull;
+        if (t == 0) st->hist1_ready = 0;
     }
 }
 
