@@ -206,6 +206,7 @@ class Walker:
         self.regrows = 0
         self.retries = 0
         self._walk_args = None
+        self.first_row_len = None      # longest restart row of the walk matrix, when known on the host (see walk())
         self.hint_override = None      # tests pin the kernel sizing through this
         self._create()
 
@@ -256,6 +257,10 @@ class Walker:
         """imputation.py:112-119 on the device.  Arguments: CSR triplets of the NormCC matrix
         (numpy arrays or torch tensors, pinned for asynchronous upload) and markers_first_order()."""
         torch = _torch()
+        self.first_row_len = None
+        if isinstance(indptr, np.ndarray) and isinstance(new_of_old, np.ndarray) and self.n_shards == 1:
+            # a row of P has the entries of the matrix row, minus a diagonal entry, plus a self-loop when isolated
+            self.first_row_len = int(np.diff(indptr)[new_of_old < self.m].max()) + 1
         with torch.cuda.device(self.device):
             d_ip = self._to_device(indptr, torch.int64)
             d_ix = self._to_device(indices, torch.int32)
@@ -283,6 +288,7 @@ class Walker:
         if P.nnz > self.pcap:
             self.pcap = int(P.nnz)
             self._recreate()
+        self.first_row_len = int(np.diff(P.indptr[:self.m + 1]).max()) if self.n_shards == 1 and self.m > 0 else None
         with torch.cuda.device(self.device):
             d_ip = self._to_device(P.indptr.astype(np.int32, copy=False), torch.int32)
             d_ix = self._to_device(P.indices.astype(np.int32, copy=False), torch.int32)
@@ -332,13 +338,18 @@ class Walker:
         _lib.check(self.lib.crwr_walk_poll(self.handle, C.byref(st), self._stream()))
         return st
 
-    def walk(self, rp, perc, tol=DEFAULT_TOL, max_steps=DEFAULT_MAX_STEPS) -> Status:
-        """Run utility.py:281-304 to completion on this GPU (unsharded walk)."""
+    def walk(self, rp, perc, tol=DEFAULT_TOL, max_steps=DEFAULT_MAX_STEPS, first_row_len: Optional[int] = None) -> Status:
+        """Run utility.py:281-304 to completion on this GPU (unsharded walk).
+
+        ``first_row_len``: longest row of the walk matrix among the restart rows, when the caller knows it (step 0
+        copies those rows, so the kernel sizing of step 1 needs no status poll after step 0)."""
         torch = _torch()
+        if first_row_len is None:
+            first_row_len = self.first_row_len
         with torch.cuda.device(self.device):
             while True:
                 try:
-                    return self._walk_once(rp, perc, tol, max_steps)
+                    return self._walk_once(rp, perc, tol, max_steps, first_row_len)
                 except CapacityError:
                     if self.cap > 256 * default_iterate_cap(self.rows, self.n):    # not a sizing problem any more
                         raise
@@ -348,14 +359,19 @@ class Walker:
                 except RetryError:
                     self.retries += 1        # rows were deferred behind a step that queued no large-row kernel
 
-    def _walk_once(self, rp, perc, tol, max_steps) -> Status:
+    def _walk_once(self, rp, perc, tol, max_steps, first_row_len=None) -> Status:
         self.walk_init(rp, perc, tol, max_steps)
         lib, h = self.lib, self.handle
         issued = 0
         hints = next_row_hints(0, 0, perc, 0)
+        if first_row_len is not None and first_row_len > 0:
+            # steps 0 and 1 in one chunk: step 0 stores the restart rows of P (+ the restart entry), step 1 is sized from that
+            hints = next_row_hints(int(first_row_len) + 1, 1, perc, 1)
         while True:
             # steps 0 and 1 change the row shapes most: poll after each; later run four at a time
             chunk = poll_chunk(issued)
+            if issued == 0 and first_row_len is not None and first_row_len > 0:
+                chunk = 2
             chunk = min(chunk, max_steps - issued)
             self.set_row_hints(*hints)
             _lib.check(lib.crwr_walk_enqueue(h, chunk, self._stream()))
@@ -555,7 +571,8 @@ def crwr_impute(normcc, marker_idx_sorted, rp, perc, tol: float = DEFAULT_TOL, m
             new_of_old = markers_first_order(n, idx)
             nnz_p = w.build_transition(d_ip, d_ix, d_dt, new_of_old)
             del d_ip, d_ix, d_dt
-            st = w.walk(rp, perc, tol, max_steps)
+            # (a row of P has the entries of the matrix row, minus a diagonal entry, plus a self-loop when isolated)
+            st = w.walk(rp, perc, tol, max_steps, first_row_len=int(np.diff(M.indptr)[idx].max()) + 1)
             ip, ix, dt = w.result_device()
             e_ip, e_ix, e_dt = symmetrise_device(ip, ix, dt, m)
             E = download_csr(e_ip, e_ix, e_dt, (m, m))

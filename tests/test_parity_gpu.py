@@ -471,7 +471,7 @@ def test_deferred_rows_behind_a_window_step_are_retried(cuda_device):
 
     class LateTinyHints(pkg.Walker):
         def set_row_hints(self, max_row_len, max_kept):
-            if max_row_len > 0 and getattr(self, "_calls", 0) >= 3 and self.retries == 0:
+            if max_row_len > 0 and getattr(self, "_calls", 0) >= 2 and self.retries == 0:      # the chunk from walk step 4 on
                 max_row_len, max_kept = 24, 6
             self._calls = getattr(self, "_calls", 0) + 1
             super().set_row_hints(max_row_len, max_kept)
