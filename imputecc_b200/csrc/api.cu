@@ -360,7 +360,7 @@ int configure_struct_shape(crwr_handle_s* h, long long max_row_len, long long ma
     // shared-memory staging for rows of up to ~16 products per output (longer rows stage in global memory)
     const double avg_deg = h->p_nnz > 0 ? (double)h->p_nnz / (double)n : 8.0;
     for (;;) {
-        if (no > 65504) no = 65504;
+        if (no > 32736) no = 32736;            // an output position travels in 15 bits of a stream entry (bit 15 flags a list end)
         if (km > no) km = no;
         long long H = 512;
         while (H < 2 * no + 64) H <<= 1;
