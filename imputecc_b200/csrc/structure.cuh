@@ -519,9 +519,9 @@ __global__ void __launch_bounds__(kBigGroups * 32) propagate_fast_big_kernel(Pro
 //   P2  hash table of the output set (K+ itself, the restart column, every column a product reaches) with the number
 //       of products per output; slot and operand of every product are remembered
 //   P3  outputs sorted by count, descending (counting sort); block offsets
-//   P4  the products into one staging list per output, IN STREAM ORDER: the operands are taken in windows of 32; the
+//   P4  the products into one staging list per output, IN STREAM ORDER: the operands are taken in windows of 64; the
 //       products of a window set their operand's bit in the output's window mask, a product's place is the output's
-//       fill level before the window plus the number of lower bits in the mask
+//       fill level before the window plus the number of lower bits in the mask (windows of 64 operands, 64-bit masks)
 //   P5  pool block: the outputs dealt to groups and lanes, the lanes' products written as the groups' streams (the
 //       writer walks the rounds exactly as the reader will); fixed slot; header
 //   P6  numeric pass, fused into P5: the lane that copies a product also adds it
@@ -540,7 +540,7 @@ struct SymShape {
 };
 __host__ __device__ inline size_t sym_smem_bytes(int H, int no_max, int km, int tmp_smem, size_t s) {
     const size_t nbm = (size_t)(no_max + 31) / 32;
-    return align16((size_t)H * 4) * 3 + align16((size_t)H * 2) +     // hkey, hcnt, wmask, hpos
+    return align16((size_t)H * 4) * 2 + align16((size_t)H * 8) + align16((size_t)H * 2) +     // hkey, hcnt, wmask, hpos
            align16((size_t)km * 4) * 2 + align16((size_t)km * s) + align16((size_t)(km + 2) * 4) * 2 +   // kcol, kps, kval, kpre, bins
            align16((size_t)km * 2) * 2 +                              // kslot, kpos
            align16((size_t)no_max * 2) * 3 +                          // olist, oslot, cnt_s
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
     unsigned char* p = smem_raw;
     int32_t* hkey = reinterpret_cast<int32_t*>(p);      p += align16((size_t)H * 4);
     int32_t* hcnt = reinterpret_cast<int32_t*>(p);      p += align16((size_t)H * 4);
-    uint32_t* wmask = reinterpret_cast<uint32_t*>(p);   p += align16((size_t)H * 4);
+    unsigned long long* wmask = reinterpret_cast<unsigned long long*>(p);   p += align16((size_t)H * 8);
     uint16_t* hpos = reinterpret_cast<uint16_t*>(p);    p += align16((size_t)H * 2);
     int32_t* kcol = reinterpret_cast<int32_t*>(p);      p += align16((size_t)KM * 4);
     int32_t* kps = reinterpret_cast<int32_t*>(p);       p += align16((size_t)KM * 4);
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
     T* kval_u = q_s;
 
     for (int i = tid; i < kHistWin; i += nth) win[i] = 0u;
-    for (int i = tid; i < H; i += nth) { hkey[i] = -1; hcnt[i] = 0; wmask[i] = 0u; }
+    for (int i = tid; i < H; i += nth) { hkey[i] = -1; hcnt[i] = 0; wmask[i] = 0ull; }
     if (tid == 0) { s_wn = 0u; s_slot_left = 0ull; s_pool_left = 0ull; s_slot_base = 0ull; s_pool_base = 0ull; }
     pdl_wait();
     WalkState* st = a.st;
@@ -748,19 +748,29 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
             // ---- P2: the output set and the products per output
             for (int i = tid; i < nk; i += nth) kslot[i] = (uint16_t)insert(kcol[i]);
             if (tid == 0) insert(dcol);
-            // a warp per operand: its P row is read coalesced; product i = kpre[k] + e of the stream
-            for (int k = warp; k < nk; k += W) {
-                const int ps = kps[k], i0 = kpre[k], ln = kpre[k + 1] - i0;
-                for (int e = lane; e < ln; e += 32) {
-                    int sl = 0;
-                    if (s_nout <= NOMAX) {
-                        const int32_t j = __ldg(pcols + ps + e);
-                        CRWR_CHECK(st, j >= 0, 5);
-                        sl = insert(j);
-                        atomicAdd(&hcnt[sl], 1);
+            // a warp per operand: its P row is read coalesced; product i = kpre[k] + e of the stream.  The first 32 entries of
+            // the warp's next operand are requested before the current operand's are inserted.
+            {
+                int k = warp;
+                int32_t j_n = -1;
+                if (k < nk && lane < kpre[k + 1] - kpre[k]) j_n = __ldg(pcols + kps[k] + lane);
+                for (; k < nk; k += W) {
+                    const int ps = kps[k], i0 = kpre[k], ln = kpre[k + 1] - i0;
+                    int32_t j = j_n;
+                    const int kn = k + W;
+                    j_n = -1;
+                    if (kn < nk && lane < kpre[kn + 1] - kpre[kn]) j_n = __ldg(pcols + kps[kn] + lane);
+                    for (int e = lane; e < ln; e += 32) {
+                        if (e >= 32) j = __ldg(pcols + ps + e);
+                        int sl = 0;
+                        if (s_nout <= NOMAX) {
+                            CRWR_CHECK(st, j >= 0, 5);
+                            sl = insert(j);
+                            atomicAdd(&hcnt[sl], 1);
+                        }
+                        pslot[i0 + e] = (uint16_t)sl;
+                        pk[i0 + e] = (uint16_t)k;
                     }
-                    pslot[i0 + e] = (uint16_t)sl;
-                    pk[i0 + e] = (uint16_t)k;
                 }
             }
             __syncthreads();
@@ -886,15 +896,15 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
         const int dpos = hpos[find(dcol)];
         __syncthreads();
         // ---- P4: the products into the staging lists, in stream order, one window of 32 operands at a time
-        for (int w0 = 0; w0 < nk; w0 += 32) {
-            const int i_lo = kpre[w0], i_hi = kpre[min(w0 + 32, nk)];
-            for (int i = i_lo + tid; i < i_hi; i += nth) atomicOr(&wmask[pslot[i]], 1u << ((int)pk[i] - w0));
+        for (int w0 = 0; w0 < nk; w0 += 64) {
+            const int i_lo = kpre[w0], i_hi = kpre[min(w0 + 64, nk)];
+            for (int i = i_lo + tid; i < i_hi; i += nth) atomicOr(&wmask[pslot[i]], 1ull << ((int)pk[i] - w0));
             __syncthreads();
             for (int i = i_lo + tid; i < i_hi; i += nth) {
                 const int sl = pslot[i], k = pk[i];
-                const unsigned bit = 1u << (k - w0);
+                const unsigned long long bit = 1ull << (k - w0);
                 const int pos = hpos[sl];
-                const int at = bptr_s[pos >> 5] + cptr[pos] + hcnt[sl] + __popc(wmask[sl] & (bit - 1u));
+                const int at = bptr_s[pos >> 5] + cptr[pos] + hcnt[sl] + __popcll(wmask[sl] & (bit - 1ull));
                 CRWR_CHECK(st, at >= 0 && at < nprod, 9);
                 tck[at] = kpos[k];
                 tcw[at] = __ldg(pvals + kps[k] + (i - kpre[k]));
@@ -902,10 +912,10 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
             __syncthreads();
             for (int i = i_lo + tid; i < i_hi; i += nth) {
                 const int sl = pslot[i];
-                const unsigned m = wmask[sl];
-                const unsigned bit = 1u << ((int)pk[i] - w0);
+                const unsigned long long m = wmask[sl];
+                const unsigned long long bit = 1ull << ((int)pk[i] - w0);
                 // the output's first product of the window updates its fill level (a later one may already see the mask cleared)
-                if (m != 0u && (m & (bit - 1u)) == 0u) { hcnt[sl] += __popc(m); wmask[sl] = 0u; }
+                if (m != 0ull && (m & (bit - 1ull)) == 0ull) { hcnt[sl] += __popcll(m); wmask[sl] = 0ull; }
             }
             __syncthreads();
         }
