@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcrwr_b200.so")
 SOURCES = ["api.cu"]
-DEPS = ["api.cu", "common.cuh", "propagate.cuh", "propagate_group.cuh", "structure.cuh", "tail.cuh", "select.cuh", "transition.cuh", "finish.cuh", "peer.cuh", "binweights.cuh",
+DEPS = ["api.cu", "common.cuh", "propagate.cuh", "propagate_group.cuh", "structure.cuh", "structure_warp.cuh", "tail.cuh", "select.cuh", "transition.cuh", "finish.cuh", "peer.cuh", "binweights.cuh",
         os.path.join("..", "..", "include", "crwr_b200.h")]
 
 

@@ -15,6 +15,7 @@
 #include "propagate.cuh"
 #include "propagate_group.cuh"
 #include "tail.cuh"
+#include "structure_warp.cuh"
 #include "transition.cuh"
 #include "finish.cuh"
 #include "peer.cuh"
@@ -97,7 +98,7 @@ struct Layout {
     size_t d_acc, d_oldv, d_ord, d_tbits, d_kbits;
     size_t k1_row_cnt, k1_col_cnt, k1_col_ptr, k1_col_fill, k1_csc_row, k1_csc_val, k1_scale, k1_iso, k1_row_val;
     size_t k1_bad;
-    size_t rs, slow_list, pool, sym_tmp;
+    size_t rs, slow_list, slow_list2, pool, sym_tmp;
     size_t pool_bytes;
     long long fixed_base, slot_cap; // first entry / entries of the fixed-slot region behind the per-step entries of both iterate buffers
     int sym_tmp_cap;                // products per staging region of the symbolic kernel
@@ -181,6 +182,7 @@ bool make_layout(const crwr_config& c, Layout& L) {
     // can hold (running out is a capacity error: the host regrows the workspace).
     L.rs = bump(off, sizeof(RowStruct) * (size_t)rows);
     L.slow_list = bump(off, 4 * (size_t)rows);
+    L.slow_list2 = bump(off, 4 * (size_t)rows);
     {
         long long pb = (long long)(c.dtype == CRWR_F64 ? 80 : 48) * cap;
         if (pb < (64ll << 20)) pb = 64ll << 20;
@@ -246,6 +248,9 @@ struct crwr_handle_s {
     bool fb_seen = false;                       // this walk has deferred rows before (polled)
     SymShape sym = {0, 0, 0, 0, 0, 0, 0, 0};    // sizing of the symbolic kernel (structure.cuh)
     int sym_grid = 0;
+    WarpSymShape wsym = {};                     // sizing of the warp-per-row symbolic kernel (structure_warp.cuh); warps 0: not used
+    int wsym_grid = 0;
+    int warp_sym = 1;                           // CRWR_WARP_SYM=0: short rows are built by the CTA kernel too
     int fast_no = 0, fast_grid = 0;             // fast kernel: outputs per row it holds (0: kernel unusable), persistent grid
     FastShape fshape = {0, 0, 0, 0};
     size_t big_smem = 0;                        // big-row kernel (structure.cuh): shared memory, persistent grid
@@ -390,6 +395,32 @@ int configure_struct_shape(crwr_handle_s* h, long long max_row_len, long long ma
     if (grid < 1) grid = 1;
     h->sym = sh;
     h->sym_grid = (int)grid;
+    // short rows, first build: a warp per row (structure_warp.cuh).  The tables are sized from the MEAN row (2.2 x its stored
+    // entries, a quarter of that in operands, products for the mean length of a P row) - a warp's shared memory decides how
+    // many rows are in flight; whatever is larger goes to the CTA kernel above.  The CTA size that keeps most warps on an SM.
+    h->wsym.warps = 0;
+    if (h->warp_sym && h->mean_row > 0 && h->mean_row <= 200) {
+        long long now = round_up((long long)(2.2 * (double)h->mean_row) + 32, 32);
+        if (now < 128) now = 128;
+        long long kw = round_up(now / 4, 32);
+        if (kw < 64) kw = 64;
+        long long pw = round_up((long long)((double)kw * avg_deg * 1.1) + 64, 64);
+        if (pw < 512) pw = 512;
+        if (pw > 2048) pw = 2048;
+        int best_w = 0, best_warps = 0, best_per_sm = 0;
+        for (int w = 2; w <= kWarpSymMaxWarps; ++w) {
+            const WarpSymShape c = warp_sym_shape<T>((int)kw, (int)pw, (int)now, w);
+            if (c.smem + 1024 > (size_t)h->max_smem_optin) break;
+            if (raise_smem_attr(symbolic_warp_kernel<T>, c.smem) != cudaSuccess) break;
+            int ps = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, symbolic_warp_kernel<T>, w * 32, c.smem) != cudaSuccess) break;
+            if (ps * w > best_warps) { best_warps = ps * w; best_w = w; best_per_sm = ps; }
+        }
+        if (best_w > 0) {
+            h->wsym = warp_sym_shape<T>((int)kw, (int)pw, (int)now, best_w);
+            h->wsym_grid = best_per_sm * h->sm_count;
+        }
+    }
     // the fast kernel stages a row's previous values and the hot part of its pool block in shared memory, two stages
     // per warp.  Sized for 2.5x the mean block observed so far (the few longer rows are read from global memory), at
     // most for the longest row the symbolic kernel stages, and shrunk until two CTAs fit an SM.
@@ -427,7 +458,10 @@ int configure_struct_shape(crwr_handle_s* h, long long max_row_len, long long ma
             h->big_smem = bs;
             h->big_grid = big_per_sm * h->sm_count;
             if (h->timeline)
-                fprintf(stderr, "shapes: fast no_max %d hot_max %d stage %zu smem %zu CTAs/SM %d (mean hot %lld) | symbolic H %d no_max %d km %d tmp_smem %d smem %zu grid %d\n",
+                fprintf(stderr, "warp symbolic: kw %d pw %d now %d hw %d rmax %d warps %d per_warp %u smem %zu grid %d\n", h->wsym.kw, h->wsym.pw,
+                    h->wsym.now, h->wsym.hw, h->wsym.rmax, h->wsym.warps, h->wsym.per_warp, h->wsym.smem, h->wsym_grid);
+            if (h->timeline)
+            fprintf(stderr, "shapes: fast no_max %d hot_max %d stage %zu smem %zu CTAs/SM %d (mean hot %lld) | symbolic H %d no_max %d km %d tmp_smem %d smem %zu grid %d\n",
                         f.no_max, f.hot_max, f.stage, f.smem, per_sm, h->avg_hot, sh.H, sh.no_max, sh.km, sh.tmp_smem, sh.smem, h->sym_grid);
         }
     }
@@ -686,6 +720,19 @@ int launch_propagate(crwr_handle_s* h, int parity, bool fused, bool win_step, cu
             // the symbolic kernel walks the rows the fast kernel handed over
             a.row_order = h->at<int32_t>(h->L.slow_list);
             a.row_list_count = &h->at<WalkState>(h->L.state)->slow_count;
+        }
+        if (h->wsym.warps > 0 && step == h->build_step) {
+            // the first build of short rows: a warp each (a single row is built sooner by a CTA, so later lists go straight
+            // to the CTA kernel); what exceeds a warp's tables comes back through the second list
+            int32_t* list2 = h->at<int32_t>(h->L.slow_list2);
+            int wgrid = (rows + h->wsym.warps - 1) / h->wsym.warps;
+            if (wgrid > h->wsym_grid) wgrid = h->wsym_grid;
+            launch_k(pdl, symbolic_warp_kernel<T>, wgrid, h->wsym.warps * 32, h->wsym.smem, st, a, h->wsym, list2);
+            ++g_launches;
+            if (cudaGetLastError() != cudaSuccess) return -1;
+            tl_mark(h, st, "symbolic (warp)");
+            a.row_order = list2;
+            a.row_list_count = &h->at<WalkState>(h->L.state)->slow2_count;
         }
         const SymShape& sh = h->sym;
         int grid = rows < h->sym_grid ? rows : h->sym_grid;
@@ -1023,6 +1070,7 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     if (h->struct_mode < 0 || h->struct_mode > 2) h->struct_mode = 1;
     h->struct_min_row = env_int("CRWR_STRUCT_MIN_ROW", 256);
     h->timeline = env_int("CRWR_TIMELINE", 0) != 0;
+    h->warp_sym = env_int("CRWR_WARP_SYM", 1);
     h->build_step = env_int("CRWR_BUILD_STEP", 3);
     if (h->build_step < 2) h->build_step = 2;       // structures only exist behind a cut
     h->win_step = env_int("CRWR_WIN_STEP", 6);

@@ -112,7 +112,7 @@ struct WalkState {
     unsigned int tick_dense, tick_hist1, tick_gather;   // last-CTA tickets
     unsigned int tick_prop;
     int32_t peer_timeout;              // a cross-GPU barrier timed out (a peer rank is gone): the walk stops
-    int32_t pad5;
+    unsigned int slow2_count;          // rows the warp-per-row symbolic kernel handed to the CTA kernel this step
     int32_t debug_error;               // CRWR_DEBUG_CHECKS builds: highest failed bounds-check code (0 = none)
     int32_t order_hazard;              // sticky: unordered rows would have been consumed without a cut (never for positive data)
     int32_t scan_done;                 // the level scans of this step already ran (in the propagate kernel's last CTA)

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(1024) peer_tail_kernel(FinishArgs a, PeerInfo 
         st->cursor = 0; st->nnz_exact = 0; st->nnz_in = 0; st->max_row_len = 0; st->max_kept = 0;
         st->row_counter = 0; st->fb_counter = 0; st->fb_count = 0;
         st->sq_limb[0] = 0; st->sq_limb[1] = 0; st->sq_limb[2] = 0;
-        st->slow_count = 0; st->fast_rows = 0; st->built_rows = 0; st->win_below = 0;
+        st->slow_count = 0; st->slow2_count = 0; st->fast_rows = 0; st->built_rows = 0; st->win_below = 0;
         st->tick_dense = 0; st->tick_hist1 = 0; st->tick_gather = 0; st->tick_prop = 0;
         st->scan_done = 0; st->hist1_ready = 0; st->unordered_rows = 0;
         st->win_on = 0;

@@ -414,7 +414,7 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
         st->tick_dense = 0; st->tick_hist1 = 0; st->tick_gather = 0; st->tick_prop = 0;
         st->scan_done = 0;
         st->hist1_ready = 0;
-        st->slow_count = 0; st->fast_rows = 0; st->built_rows = 0; st->win_below = 0;
+        st->slow_count = 0; st->slow2_count = 0; st->fast_rows = 0; st->built_rows = 0; st->win_below = 0;
         if (cut_applied) {      // the next cut most likely falls into the same level-0 bin
             st->pred_prefix0 = (unsigned long long)(KO::enc((T)cut) >> (KO::bits - kSelectBits));
             st->pred_valid = 1;

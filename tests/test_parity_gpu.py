@@ -451,7 +451,8 @@ def test_cached_structures_and_window_select_change_no_bit(cuda_device, dtype, m
                                  {"CRWR_WIN_MIN": "1e-7", "CRWR_WIN_SCALE": "0.01"},   # windows that miss: full select in the tail
                                  {"CRWR_WIN_STEP": "2", "CRWR_WIN_REL_MAX": "10", "CRWR_WIN_MAX": "0.9"},   # window select from the first cut on
                                  {"CRWR_STRUCT_ALPHA": "1.0"},                        # K+ = K: structures fall out of date often
-                                 {"CRWR_STRUCT_ALPHA": "0.05"}])                      # very wide K+
+                                 {"CRWR_STRUCT_ALPHA": "0.05"},                       # very wide K+
+                                 {"CRWR_WARP_SYM": "0"}])                             # first build by the CTA kernel (default for short rows: a warp per row)
 def test_structure_and_window_corner_policies_change_no_bit(cuda_device, env, monkeypatch):
     M, idx = synth.make_workload(synth.Workload("cs", 5000, 800, 100, 16))
     steps0, it0, tr0, _ = _walk(M, idx, np.float32, cuda_device)
@@ -459,6 +460,33 @@ def test_structure_and_window_corner_policies_change_no_bit(cuda_device, env, mo
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     steps, it, tr, _ = _walk(M, idx, np.float32, cuda_device)
+    assert steps == steps0 and _trace_key(tr) == _trace_key(tr0)
+    assert _bit_equal(it, it0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_warp_built_structures_hand_long_rows_to_the_cta_kernel(cuda_device, dtype, monkeypatch):
+    """Short rows get their structure from the warp-per-row kernel (structure_warp.cuh), whose tables follow the MEAN row;
+    the rows of a few hub markers and of their neighbours, several times longer, exceed them and come back through the second list.  Same bits as the
+    hash-accumulating kernels."""
+    import scipy.sparse as sp
+    M, idx = synth.make_workload(synth.Workload("hub", 6000, 900, 100, 16))
+    rng = np.random.default_rng(7)
+    n = M.shape[0]
+    hubs = idx[rng.choice(idx.size, 3, replace=False)]
+    rows = np.repeat(hubs, 300)
+    cols = rng.integers(0, n, rows.size)
+    keep = rows != cols
+    add = sp.coo_matrix((rng.integers(1, 2, keep.sum()).astype(M.dtype), (rows[keep], cols[keep])), shape=M.shape).tocsr()
+    add.sum_duplicates()
+    M2 = (M + add + add.T).tocsr()
+    M2.sort_indices()
+    monkeypatch.setenv("CRWR_STRUCT", "0")
+    steps0, it0, tr0, _ = _walk(M2, idx, dtype, cuda_device)
+    assert max(t["max_row_len"] for t in tr0) > 3 * (tr0[3]["nnz_new"] // idx.size)       # well above the mean (the tables hold 2.2 x)
+    monkeypatch.setenv("CRWR_STRUCT", "2")
+    steps, it, tr, _ = _walk(M2, idx, dtype, cuda_device)
+    assert sum(t["fast_rows"] for t in tr[4:]) > 0.7 * idx.size * (len(tr) - 5)
     assert steps == steps0 and _trace_key(tr) == _trace_key(tr0)
     assert _bit_equal(it, it0)
 
