@@ -58,9 +58,13 @@ __host__ __device__ inline StructLayout struct_layout(int no, int nprod, int G) 
     L.bytes = (o + 15u) & ~15u;
     return L;
 }
+// The chunks of 32 outputs are dealt to the groups round by round in alternating direction, like the outputs of a chunk
+// to the lanes: the counts fall from chunk to chunk, so a plain round robin would give group 0 the heaviest chunk of
+// every round.  ii-th chunk of group g:
+__device__ __forceinline__ int chunk_of(int ii, int g, int G) { return ii * G + ((ii & 1) ? G - 1 - g : g); }
 // Position of the output that lane `lane` of group g owns in the group's ii-th chunk (the direction alternates).
 __device__ __forceinline__ int lane_pos(int ii, int g, int G, int lane) {
-    return ((ii * G + g) << 5) + ((ii & 1) ? 31 - lane : lane);
+    return (chunk_of(ii, g, G) << 5) + ((ii & 1) ? 31 - lane : lane);
 }
 
 // ---- bulk asynchronous copies global -> shared (TMA, cp.async.bulk) completing on an mbarrier
@@ -211,12 +215,14 @@ __device__ __forceinline__ void numeric_stream(const PropArgs<T>& a, const unsig
     int off = NC ? __ldg(gptr + g) : gptr[g];
     const int rounds = __reduce_max_sync(kFull, load);
     // The sums are parked by (chunk of the group, owning lane): res_s[ii * 32 * G + g * 32 + lane] - the group's ii-th
-    // chunk occupies the 32 entries of chunk ii * G + g.  Outputs without a product keep 0.
-    for (int c = g; c < nb; c += G) res_s[(c << 5) + lane] = (T)0;
+    // chunk occupies the 32 entries of chunk chunk_of(ii, g, G).  Outputs without a product keep 0.
+    for (int ii = 0, c; (c = chunk_of(ii, g, G)) < nb; ++ii) res_s[(c << 5) + lane] = (T)0;
     __syncwarp();
     T acc = (T)0;
     T* res_cur = res_s + (g << 5) + lane;
-    const int res_step = G << 5;
+    // (from an even chunk of the group to the next odd one and back: chunk_of)
+    int res_step = (2 * G - 1 - 2 * g) << 5;
+    const int res_flip = ((2 * G - 1 - 2 * g) << 5) ^ ((2 * g + 1) << 5);
     for (int j0 = 0; j0 < rounds; j0 += RN) {
         unsigned e[RN];
         T w[RN];
@@ -233,7 +239,7 @@ __device__ __forceinline__ void numeric_stream(const PropArgs<T>& a, const unsig
         for (int r = 0; r < RN; ++r) {
             if (j0 + r < load) {
                 acc = add_rn(acc, mul_rn(q_s[e[r] & (kLastFlag - 1u)], w[r]));
-                if (e[r] & kLastFlag) { *res_cur = acc; res_cur += res_step; acc = (T)0; }
+                if (e[r] & kLastFlag) { *res_cur = acc; res_cur += res_step; res_step ^= res_flip; acc = (T)0; }
             }
         }
     }
@@ -242,7 +248,7 @@ __device__ __forceinline__ void numeric_stream(const PropArgs<T>& a, const unsig
     Sq128 sq = tot.sq;
     int nz = 0;
     int ii = 0;
-    for (int c = g; c < nb; c += G, ++ii) {
+    for (int c; (c = chunk_of(ii, g, G)) < nb; ++ii) {
         const int p = (c << 5) + lane;
         const bool act = p < no;
         T v = (T)0;
@@ -450,7 +456,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) propagate_fast_kernel(PropArg
 // follows skips them.  fs: the fast kernel's stage limits (a row that fits them is left to it).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kBigGroups * 32) propagate_fast_big_kernel(PropArgs<T> a, FastShape fs, int NQ) {
+__global__ void __launch_bounds__(kBigGroups * 32, 4) propagate_fast_big_kernel(PropArgs<T> a, FastShape fs, int NQ) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned int s_wn;
     __shared__ int s_nkept;
@@ -929,7 +935,7 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
         T* cw_w = reinterpret_cast<T*>(blk + L.cw);
         for (int g = warp; g < G; g += W) {
             int sum = 0;
-            for (int ii = 0; ii * G + g < nb; ++ii) {
+            for (int ii = 0; chunk_of(ii, g, G) < nb; ++ii) {
                 const int pp = lane_pos(ii, g, G, lane);
                 if (pp < no) sum += (int)cnt_s[pp];
             }
@@ -980,7 +986,7 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
                         acc = (T)0;
                         ++ii; c = 0;
                         pp = lane_pos(ii, g, G, lane);
-                        const bool have = ii * G + g < nb && pp < no;
+                        const bool have = chunk_of(ii, g, G) < nb && pp < no;
                         cntp = have ? (int)cnt_s[pp] : 0;
                         src = have ? bptr_s[pp >> 5] + cptr[pp] : 0;
                     } else ++c;
@@ -989,7 +995,7 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
             }
             __syncwarp();
             int nz = 0;
-            for (int ch = g; ch < nb; ch += G) {
+            for (int i2 = 0, ch; (ch = chunk_of(i2, g, G)) < nb; ++i2) {
                 const int q = (ch << 5) + lane;
                 const bool act = q < no;
                 T v = (T)0;
