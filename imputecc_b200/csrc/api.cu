@@ -243,6 +243,8 @@ struct crwr_handle_s {
     bool sharded_window_ok = false;             // sharded walk: the last poll saw a window narrow enough for the push regions
     int win_step_sharded = 9;
     float alpha = 0.5f;                         // K+ = entries above alpha x cut (CRWR_STRUCT_ALPHA)
+    float alpha_build = 0.4f;                   // the same for the first build (CRWR_STRUCT_ALPHA_BUILD, default 0.8 x alpha): the rows are
+                                                // still growing then, a wider K+ keeps a quarter of them from being rebuilt in the next steps
     float win_scale = 2.5f, win_min = 0.004f, win_max = 0.15f, win_rel_max = 0.10f;
     bool dense_always = false;                  // a step deferred rows while no large-row kernel was queued: always queue it
     bool fb_seen = false;                       // this walk has deferred rows before (polled)
@@ -621,7 +623,7 @@ PropArgs<T> prop_args(crwr_handle_s* h, int parity, bool fused) {
     a.pool = h->at<unsigned char>(L.pool);
     a.pool_cap = (unsigned long long)L.pool_bytes;
     a.slow_list = h->at<int32_t>(L.slow_list);
-    a.alpha = h->alpha;
+    a.alpha = h->steps_enqueued == h->build_step ? h->alpha_build : h->alpha;
     a.fixed_base = L.fixed_base;
     a.slot_cap = L.slot_cap;
     a.sym_tmp = h->at<unsigned char>(L.sym_tmp);
@@ -1081,6 +1083,8 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     if (h->prop_kind != 1) h->win_step = 0;         // the warp-per-row kernel only knows the histogram select
     h->alpha = (float)env_double("CRWR_STRUCT_ALPHA", 0.5);
     if (!(h->alpha > 0.f && h->alpha <= 1.f)) h->alpha = 0.5f;
+    h->alpha_build = (float)env_double("CRWR_STRUCT_ALPHA_BUILD", 0.8 * (double)h->alpha);
+    if (!(h->alpha_build > 0.f && h->alpha_build <= 1.f)) h->alpha_build = h->alpha;
     h->win_scale = (float)env_double("CRWR_WIN_SCALE", 2.5);
     h->win_min = (float)env_double("CRWR_WIN_MIN", 0.004);
     h->win_max = (float)env_double("CRWR_WIN_MAX", 0.15);
