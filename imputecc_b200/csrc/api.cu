@@ -234,7 +234,8 @@ struct crwr_handle_s {
     bool hist0_fused = false;                   // sharded step: level-0 histogram already filled by propagate
     int struct_mode = 1;                        // CRWR_STRUCT: 0 no cached row structures (row-group kernel every step), 1 when
                                                 // the rows are long enough to pay for them (default), 2 always
-    long long struct_min_row = 256;             // ... mean stored entries per row from which they pay (CRWR_STRUCT_MIN_ROW)
+    long long struct_min_row = 176;             // ... mean stored entries per row (at the last poll before the build: walk step 1)
+                                                // from which they pay (CRWR_STRUCT_MIN_ROW; measured crossover 161 / 191, profiles/bench_r2.md)
     long long mean_row = 0;                     // mean stored entries per row at the last poll
     bool structs_active = false;                // this walk's decision, taken when the first structure step is queued
     bool redo_hist = false;                     // sharded walk: the next step repeats one whose window missed (histogram select)
@@ -397,11 +398,12 @@ int configure_struct_shape(crwr_handle_s* h, long long max_row_len, long long ma
     if (grid < 1) grid = 1;
     h->sym = sh;
     h->sym_grid = (int)grid;
-    // short rows, first build: a warp per row (structure_warp.cuh).  The tables are sized from the MEAN row (2.2 x its stored
-    // entries, a quarter of that in operands, products for the mean length of a P row) - a warp's shared memory decides how
-    // many rows are in flight; whatever is larger goes to the CTA kernel above.  The CTA size that keeps most warps on an SM.
+    // short rows, first build: a warp per row (structure_warp.cuh).  The tables are sized from the MEAN row as the last poll
+    // saw it (walk step 1; rows grow by a third until the build at step 3): 2.2 x its stored entries, a quarter of that in
+    // operands, products for the mean length of a P row - a warp's shared memory decides how many rows are in flight; whatever
+    // is larger goes to the CTA kernel above (at a mean above ~110 most rows would, after the warp has done half the work).  The CTA size that keeps most warps on an SM.
     h->wsym.warps = 0;
-    if (h->warp_sym && h->mean_row > 0 && h->mean_row <= 200) {
+    if (h->warp_sym && h->mean_row > 0 && h->mean_row <= 110) {
         long long now = round_up((long long)(2.2 * (double)h->mean_row) + 32, 32);
         if (now < 128) now = 128;
         long long kw = round_up(now / 4, 32);
@@ -480,7 +482,11 @@ int configure_group_shape(crwr_handle_s* h, long long max_row_len, long long max
                                                                   // by a quarter between the last early poll and the plateau)
     if (want < 48) want = 48;
     if (want > n + 16) want = n + 16;
-    long long kmax = round_up(max_kept + max_kept * 3 / 10 + 8, 16);
+    // (the longest kept row still grows after the last early poll: +20 % on the dense planted partitions, +30 % on the sparse
+    // ones, +50 % in between - 56 -> 84 entries at 220-contig genomes; a kept list that is too short sends the row to the
+    // large-row kernel, ~100 us per step, so rows beyond the sparse workloads' 40 entries get the larger margin)
+    const long long kept_margin = env_int("CRWR_KEPT_MARGIN_PCT", max_kept > 44 ? 50 : 30);
+    long long kmax = round_up(max_kept + max_kept * kept_margin / 100 + 8, 16);
     if (kmax < 32) kmax = 32;
     if (kmax > n) kmax = round_up(n, 16);
     const size_t win_bytes = kHistWin * sizeof(unsigned int);
@@ -494,9 +500,9 @@ int configure_group_shape(crwr_handle_s* h, long long max_row_len, long long max
     if (const char* e = getenv("CRWR_GROUP_WARPS")) { const int g = atoi(e); if (g >= 1 && g <= 8) wfix = g; }
     // overflow list entries = expected longest row / ov_div.  Long rows fill their table to the nominal load more
     // often and spill several products per overflowing column: a quarter instead of an eighth removes the large-row
-    // fallbacks of c4_dense (24 -> 1 rows per walk, -10 % per step); short rows keep the smaller list (it would cost
-    // them a CTA per SM).
-    long long ov_div = want > 512 ? 4 : 8;
+    // fallbacks of c4_dense (24 -> 1 rows per walk, -10 % per step) and of 220-contig genomes (10 rows in every step,
+    // +35 % per walk); short rows keep the smaller list (it would cost them a CTA per SM).
+    long long ov_div = want > 384 ? 4 : 8;
     if (const char* e = getenv("CRWR_GROUP_OV_DIV")) { const int v = atoi(e); if (v >= 1 && v <= 64) ov_div = v; }
     // table, kept list and CTA size for one table load
     auto make = [&](int load_pct, long long* in_flight) -> GroupShape {
@@ -1070,7 +1076,7 @@ int32_t crwr_create(crwr_handle* out, const crwr_config* cfg, void* d_workspace,
     if (const char* k = getenv("CRWR_ROW_ORDER")) h->use_order = atoi(k) != 0;
     h->struct_mode = env_int("CRWR_STRUCT", 1);
     if (h->struct_mode < 0 || h->struct_mode > 2) h->struct_mode = 1;
-    h->struct_min_row = env_int("CRWR_STRUCT_MIN_ROW", 256);
+    h->struct_min_row = env_int("CRWR_STRUCT_MIN_ROW", 176);
     h->timeline = env_int("CRWR_TIMELINE", 0) != 0;
     h->warp_sym = env_int("CRWR_WARP_SYM", 1);
     h->build_step = env_int("CRWR_BUILD_STEP", 3);

@@ -136,6 +136,7 @@ struct WalkState {
     unsigned long long win_below;      // values strictly below win_lo (this rank)
     unsigned int win_miss_steps;       // diagnostics: steps whose window missed (full select in the tail kernel)
     int32_t win_missed;                // sharded walk: the window missed, the step was rewound and the walk waits for the host
+    double win_prev_rel;               // relative move of the cut one step earlier (the window follows the larger of the last two)
 };
 
 // Exchange block 0 of a sharded walk: level-0 histogram followed by these extras (all uint64, SUM).

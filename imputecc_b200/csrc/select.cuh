@@ -362,10 +362,14 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
         // select window of the next step: the cut moves less and less, so it will lie within a few times its last move
         {
             int on = 0, narrow = 0;
-            if (a.next_win && cut_applied && st->cut_on && st->cut > 0.0) {
-                const double c0 = st->cut, c1 = cut;
-                const double rel = fabs(c1 - c0) / c1;
-                double dl = (double)a.win_scale * rel;
+            const bool moved = cut_applied && st->cut_on && st->cut > 0.0 && cut > 0.0;
+            const double rel = moved ? fabs(cut - st->cut) / cut : 0.0;
+            if (a.next_win && moved) {
+                const double c1 = cut;
+                // a settling cut does not move monotonically less: a step of 0.06 % can be followed by one of 0.4 %.  Half
+                // the move before the last is the floor (a miss costs a one-CTA select over the whole value array)
+                const double rel_w = rel > 0.5 * st->win_prev_rel ? rel : 0.5 * st->win_prev_rel;
+                double dl = (double)a.win_scale * rel_w;
                 dl = dl < (double)a.win_min ? (double)a.win_min : (dl > (double)a.win_max ? (double)a.win_max : dl);
                 const T lo = (T)(c1 * (1.0 - dl)), hi = (T)(c1 * (1.0 + dl));
                 if (rel <= (double)a.win_rel_max && lo > (T)0 && hi > lo) {
@@ -379,6 +383,7 @@ __device__ __forceinline__ void finish_step_body(const FinishArgs& a, unsigned c
             }
             st->win_on = on;
             st->win_narrow = narrow;
+            st->win_prev_rel = rel;
         }
         // rows written in slot-claim order (row-group kernel) are only valid operands behind a cut
         if (st->unordered_rows && a.do_select && !cut_applied && st->n_total > 0 && !st->capacity_overflow && !st->select_overflow)

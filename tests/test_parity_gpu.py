@@ -491,6 +491,21 @@ def test_warp_built_structures_hand_long_rows_to_the_cta_kernel(cuda_device, dty
     assert _bit_equal(it, it0)
 
 
+@pytest.mark.parametrize("genome,degree", [(160, 20), (220, 24), (300, 30)])
+def test_densities_between_the_bench_workloads_change_no_bit(cuda_device, genome, degree, monkeypatch):
+    """Genome sizes between SURVEY 8d's two densities: the default policy (structures or not by the mean row, kept-list
+    margin and overflow list by the row hints, window by the last two moves of the cut) against the plain path - row-group
+    kernel and histogram select in every step.  No row may take the large-row kernel under the default policy."""
+    M, idx = synth.make_workload(synth.Workload("mid", 12000, 1920, genome, degree))
+    steps, it, tr, _ = _walk(M, idx, np.float32, cuda_device)
+    assert all(t["fallback_rows"] == 0 for t in tr)
+    monkeypatch.setenv("CRWR_STRUCT", "0")
+    monkeypatch.setenv("CRWR_WIN_STEP", "0")
+    steps0, it0, tr0, _ = _walk(M, idx, np.float32, cuda_device)
+    assert steps == steps0 and _trace_key(tr) == _trace_key(tr0)
+    assert _bit_equal(it, it0)
+
+
 def test_deferred_rows_behind_a_window_step_are_retried(cuda_device):
     """Tiny accumulator hints from walk step 4 on: rows are deferred in a window-select step that queued no large-row
     kernel; the finish step flags it, the host walks again with the kernel queued, and the result is unchanged."""

@@ -17,9 +17,13 @@ ap.add_argument("--workload", default="c3_sparse")
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--hints", default="")
+ap.add_argument("--custom", default="", help="n_contigs,n_markers,genome_size,intra_degree instead of a named workload")
 args = ap.parse_args()
 dt = np.float64 if args.dtype == "f64" else np.float32
-M, idx = synth.make_workload(synth.WORKLOADS[args.workload])
+if args.custom:
+    M, idx = synth.make_workload(synth.Workload("custom", *[int(x) for x in args.custom.split(",")]))
+else:
+    M, idx = synth.make_workload(synth.WORKLOADS[args.workload])
 n, m = M.shape[0], idx.size
 w = pkg.Walker(n, m, dtype=dt, device="cuda:0", transition_nnz_cap=M.nnz + n)
 w.build_transition(M.indptr, M.indices, M.data, pkg.markers_first_order(n, idx))
