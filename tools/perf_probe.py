@@ -17,6 +17,8 @@ ap.add_argument("--workload", default="c3_sparse")
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--hints", default="")
+ap.add_argument("--rp", type=float, default=0.5)
+ap.add_argument("--perc", type=float, default=80)
 ap.add_argument("--custom", default="", help="n_contigs,n_markers,genome_size,intra_degree instead of a named workload")
 args = ap.parse_args()
 dt = np.float64 if args.dtype == "f64" else np.float32
@@ -34,7 +36,7 @@ for rep in range(args.reps):
     lib.crwr_profile(w.handle, 1)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    st = w.walk(0.5, 80)
+    st = w.walk(args.rp, args.perc)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     tot, nl = _lib.C.c_double(0), _lib.C.c_int64(0)
