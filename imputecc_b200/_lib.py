@@ -59,6 +59,7 @@ _SIGNATURES = {
     "crwr_transition_nnz": (C.c_int64, [_P]),
     "crwr_walk_init": (C.c_int32, [_P, C.c_double, C.c_double, C.c_double, C.c_int32, _P]),
     "crwr_set_row_hints": (C.c_int32, [_P, C.c_int64, C.c_int64]),
+    "crwr_hold_window_select": (C.c_int32, [_P, C.c_int32]),
     "crwr_get_shape": (C.c_int32, [_P, C.POINTER(C.c_int64)]),
     "crwr_get_group_shape": (C.c_int32, [_P, C.POINTER(C.c_int64)]),
     "crwr_profile": (C.c_int32, [_P, C.c_int32]),

@@ -164,6 +164,26 @@ def next_row_hints(max_row_len: int, max_kept: int, perc: float, issued: int):
     return max_row_len, max_kept
 
 
+def expanding_walk(prev, now) -> bool:
+    """Host policy at the third poll: is the walk settling (the usual case at the reference's rwr-thres 80: from step 3 on
+    the products grow by a few percent per step and the cut moves by less and less) or still expanding (rwr-thres 50 keeps
+    half of every product: rows double from step to step until they are dense, and the cut falls five-fold per step)?
+
+    ``prev`` / ``now``: (steps issued, entries of the last product, its cut) at the previous and at this poll.  For an
+    expanding walk no select window can ever be set, and the single-CTA kernel of the settled-walk form would have to
+    select over the whole value array by itself - 77 of 190 ms for 8,000 markers at rwr-thres 50 - so such a walk keeps
+    the multi-CTA histogram select (crwr_hold_window_select).  (Measured and rejected for these walks: polling after every
+    step with row hints scaled by the observed growth - the row-group kernel with tables for 20,000-column rows is slower
+    than the large-row kernel the stale hints send them to.)"""
+    steps = max(now[0] - prev[0], 1)
+    if min(prev[1], now[1]) <= 0 or min(prev[2], now[2]) <= 0.0:
+        return False
+    growth = (float(now[1]) / float(prev[1])) ** (1.0 / steps)
+    cut_ratio = (now[2] / prev[2]) ** (1.0 / steps)
+    # steps 1 -> 3 of a settling walk: x1.2 per step (sparse) to x1.4 (dense planted partitions), cut x0.55 .. 0.66
+    return growth > 1.5 and cut_ratio < 0.5
+
+
 def stack_row_blocks(blocks: Sequence[sp.csr_matrix]) -> sp.csr_matrix:
     """Concatenate per-shard row blocks (same column count) into one CSR matrix."""
     return sp.vstack(list(blocks), format="csr")
@@ -367,6 +387,7 @@ class Walker:
         if first_row_len is not None and first_row_len > 0:
             # steps 0 and 1 in one chunk: step 0 stores the restart rows of P (+ the restart entry), step 1 is sized from that
             hints = next_row_hints(int(first_row_len) + 1, 1, perc, 1)
+        prev = None                 # what the poll before saw (expanding_walk)
         while True:
             # steps 0 and 1 change the row shapes most: poll after each; later run four at a time
             chunk = poll_chunk(issued)
@@ -380,6 +401,10 @@ class Walker:
             if st.stop_reason != 0 or issued >= max_steps:
                 return st
             hints = self.row_hints(st, perc, issued)
+            now = (issued, int(st.nnz_iterate), float(st.last_cut))
+            if issued == 4 and prev is not None and expanding_walk(prev, now):
+                _lib.check(lib.crwr_hold_window_select(h, max_steps + 1))
+            prev = now
 
     def set_row_hints(self, max_row_len: int, max_kept: int):
         if self.hint_override is not None:

@@ -101,7 +101,9 @@ struct Layout {
     size_t rs, slow_list, slow_list2, pool, sym_tmp;
     size_t pool_bytes;
     long long fixed_base, slot_cap; // first entry / entries of the fixed-slot region behind the per-step entries of both iterate buffers
-    int sym_tmp_cap;                // products per staging region of the symbolic kernel
+    int sym_tmp_cap;                // products per staging region of the symbolic kernel (with the most CTAs it is launched with)
+    size_t sym_tmp_total;           // bytes of all staging regions
+    long long sym_tmp_max;          // a row has at most this many products (nnz of the transition matrix)
     size_t bytes;
     long long cand_cap;
     long long dense_warps;
@@ -196,7 +198,9 @@ bool make_layout(const crwr_config& c, Layout& L) {
         tc = (tc + 7) & ~7ll;
         L.sym_tmp_cap = (int)tc;
         const long long ctas = rows < kSymMaxCtas ? rows : kSymMaxCtas;
-        L.sym_tmp = bump(off, (size_t)ctas * sym_tmp_bytes((int)tc, s));
+        L.sym_tmp_total = (size_t)ctas * sym_tmp_bytes((int)tc, s);
+        L.sym_tmp_max = pcap;
+        L.sym_tmp = bump(off, L.sym_tmp_total);
     }
 
     L.bytes = (off + 255) & ~(size_t)255;
@@ -243,6 +247,7 @@ struct crwr_handle_s {
     bool scan_push = true;                      // sharded histogram steps exchange level 0 (+1) by pushing (CRWR_SCAN_PUSH=0: pull)
     bool sharded_window_ok = false;             // sharded walk: the last poll saw a window narrow enough for the push regions
     int win_step_sharded = 9;
+    int win_hold_until = 0;                     // host policy (crwr_hold_window_select): no window-select step before this walk step
     float alpha = 0.5f;                         // K+ = entries above alpha x cut (CRWR_STRUCT_ALPHA)
     float alpha_build = 0.4f;                   // the same for the first build (CRWR_STRUCT_ALPHA_BUILD, default 0.8 x alpha): the rows are
                                                 // still growing then, a wider K+ keeps a quarter of them from being rebuilt in the next steps
@@ -377,8 +382,14 @@ int configure_struct_shape(crwr_handle_s* h, long long max_row_len, long long ma
         if (ts > h->L.sym_tmp_cap) ts = h->L.sym_tmp_cap;
         sh.H = (int)H; sh.no_max = (int)no; sh.km = (int)km; sh.tmp_smem = (int)ts;
         sh.smem = sym_smem_bytes(sh.H, sh.no_max, sh.km, sh.tmp_smem, sizeof(T));
+        // too big for one SM: first fewer products staged in shared memory (the rest stage in global memory), only then
+        // fewer outputs - rows beyond them go to the large-row kernel, 100 us per step
+        while (sh.smem + 1024 > (size_t)h->max_smem_optin && sh.tmp_smem > 2048) {
+            sh.tmp_smem = (int)round_up(sh.tmp_smem * 3 / 4, 64);
+            sh.smem = sym_smem_bytes(sh.H, sh.no_max, sh.km, sh.tmp_smem, sizeof(T));
+        }
         if (sh.smem + 1024 <= (size_t)h->max_smem_optin) break;
-        no = round_up(no * 3 / 4, 32);          // too big for one SM: larger rows go to the large-row kernel
+        no = round_up(no * 3 / 4, 32);
     }
     sh.tmp_cap = h->L.sym_tmp_cap;
     sh.threads = env_int("CRWR_SYM_THREADS", 256);
@@ -396,6 +407,16 @@ int configure_struct_shape(crwr_handle_s* h, long long max_row_len, long long ma
     const long long max_ctas = rows < kSymMaxCtas ? rows : kSymMaxCtas;
     if (grid > max_ctas) grid = max_ctas;
     if (grid < 1) grid = 1;
+    // the staging regions are shared out among the CTAs actually launched: long rows run one CTA per SM and may have
+    // several times the products a region holds when every SM carries eight CTAs
+    {
+        long long cap = sh.tmp_cap;
+        while (cap * 2 <= h->L.sym_tmp_max * 2 && (size_t)grid * sym_tmp_bytes((int)(cap * 2), sizeof(T)) <= h->L.sym_tmp_total &&
+               cap * 2 <= (1ll << 22))
+            cap *= 2;
+        if (cap > h->L.sym_tmp_max) cap = (h->L.sym_tmp_max + 7) & ~7ll;
+        if (cap > sh.tmp_cap) sh.tmp_cap = (int)cap;
+    }
     h->sym = sh;
     h->sym_grid = (int)grid;
     // short rows, first build: a warp per row (structure_warp.cuh).  The tables are sized from the MEAN row as the last poll
@@ -844,7 +865,8 @@ FinishArgs finish_args(crwr_handle_s* h, int do_select, const void* gathered) {
     a.trace = h->at<crwr_step_record>(L.trace);
     a.do_select = do_select;
     // the step after this one is a window-select step: derive its window from this step's cut
-    a.next_win = (h->win_step > 0 && (h->cfg.n_shards == 1 || h->peer_attached) && h->steps_enqueued + 1 >= h->win_step) ? 1 : 0;
+    a.next_win = (h->win_step > 0 && (h->cfg.n_shards == 1 || h->peer_attached) && h->steps_enqueued + 1 >= h->win_step &&
+                  h->steps_enqueued + 1 >= h->win_hold_until) ? 1 : 0;
     a.dense_launched = h->dense_launched ? 1 : 0;
     a.win_scale = h->win_scale; a.win_min = h->win_min; a.win_max = h->win_max; a.win_rel_max = h->win_rel_max;
     a.win_narrow_cands = (long long)h->cfg.n_shards * (kPushCand * 3 / 4);
@@ -923,7 +945,7 @@ int enqueue_step(crwr_handle_s* h, cudaStream_t st) {
         // no percentile cut on step 0 (utility.py:286)
         if (launch_propagate<T>(h, parity, false, false, st)) return -1;
         if (launch_finish<T>(h, 0, nullptr, st)) return -1;
-    } else if (h->win_step > 0 && step >= h->win_step) {
+    } else if (h->win_step > 0 && step >= h->win_step && step >= h->win_hold_until) {
         // settled walk: propagation kernels (values classified against the select window) -> one single-CTA tail
         prof_mark(h, st, 0);
         if (launch_propagate<T>(h, parity, false, true, st)) return -1;
@@ -1229,6 +1251,7 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
     h->rp = rp;
     h->perc = perc;
     h->steps_enqueued = 0;
+    h->win_hold_until = 0;
     h->avg_hot = 0;
     h->mean_row = 0;
     h->structs_active = false;
@@ -1369,6 +1392,12 @@ int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept)
     h->hint_len = max_row_len;
     h->hint_kept = max_kept;
     h->hint_len_eff = max_row_len;
+    return CRWR_OK;
+}
+
+int32_t crwr_hold_window_select(crwr_handle h, int32_t until_step) {
+    if (!h) CRWR_FAIL(CRWR_ERR_INVALID, "null handle");
+    h->win_hold_until = until_step > 0 ? until_step : 0;
     return CRWR_OK;
 }
 
@@ -1608,7 +1637,7 @@ int32_t crwr_walk_poll(crwr_handle h, crwr_status* out, void* stream) {
     out->capacity_overflow = s.capacity_overflow | (s.select_overflow << 1) | (s.win_missed << 2);
     h->sharded_window_ok = s.win_on != 0 && s.win_narrow != 0;
     out->fallback_rows = s.last_fallback_rows;
-    out->nnz_iterate = (int64_t)s.nnz_exact;
+    out->nnz_iterate = (int64_t)s.last_nnz_new;
     out->max_row_len = s.last_max_row_len;
     out->max_kept = s.last_max_kept;
     out->last_cut = s.cut;

@@ -525,9 +525,9 @@ __global__ void __launch_bounds__(kBigGroups * 32, 4) propagate_fast_big_kernel(
 //   P2  hash table of the output set (K+ itself, the restart column, every column a product reaches) with the number
 //       of products per output; slot and operand of every product are remembered
 //   P3  outputs sorted by count, descending (counting sort); block offsets
-//   P4  the products into one staging list per output, IN STREAM ORDER: the operands are taken in windows of 64; the
+//   P4  the products into one staging list per output, IN STREAM ORDER: the operands are taken in windows of kWinOps; the
 //       products of a window set their operand's bit in the output's window mask, a product's place is the output's
-//       fill level before the window plus the number of lower bits in the mask (windows of 64 operands, 64-bit masks)
+//       fill level before the window plus the number of lower bits in the mask (one mask bit per operand of the window)
 //   P5  pool block: the outputs dealt to groups and lanes, the lanes' products written as the groups' streams (the
 //       writer walks the rounds exactly as the reader will); fixed slot; header
 //   P6  numeric pass, fused into P5: the lane that copies a product also adds it
@@ -544,9 +544,16 @@ struct SymShape {
     int tmp_cap;        // products per global staging region (one per CTA)
     size_t smem;        // dynamic shared memory per CTA (window included)
 };
+// Operands per ordering window of P4 = bits of an output's window mask.  (64-bit masks halve the windows of a long row but
+// measured no faster, and cost 4 bytes per hash slot of shared memory that long rows need for their tables.)
+typedef unsigned int WMask;
+constexpr int kWinOps = 8 * (int)sizeof(WMask);
+__device__ __forceinline__ int wmask_popc(unsigned int m) { return __popc(m); }
+__device__ __forceinline__ int wmask_popc(unsigned long long m) { return __popcll(m); }
+
 __host__ __device__ inline size_t sym_smem_bytes(int H, int no_max, int km, int tmp_smem, size_t s) {
     const size_t nbm = (size_t)(no_max + 31) / 32;
-    return align16((size_t)H * 4) * 2 + align16((size_t)H * 8) + align16((size_t)H * 2) +     // hkey, hcnt, wmask, hpos
+    return align16((size_t)H * 4) * 2 + align16((size_t)H * sizeof(WMask)) + align16((size_t)H * 2) +     // hkey, hcnt, wmask, hpos
            align16((size_t)km * 4) * 2 + align16((size_t)km * s) + align16((size_t)(km + 2) * 4) * 2 +   // kcol, kps, kval, kpre, bins
            align16((size_t)km * 2) * 2 +                              // kslot, kpos
            align16((size_t)no_max * 2) * 3 +                          // olist, oslot, cnt_s
@@ -579,7 +586,7 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
     unsigned char* p = smem_raw;
     int32_t* hkey = reinterpret_cast<int32_t*>(p);      p += align16((size_t)H * 4);
     int32_t* hcnt = reinterpret_cast<int32_t*>(p);      p += align16((size_t)H * 4);
-    unsigned long long* wmask = reinterpret_cast<unsigned long long*>(p);   p += align16((size_t)H * 8);
+    WMask* wmask = reinterpret_cast<WMask*>(p);         p += align16((size_t)H * sizeof(WMask));
     uint16_t* hpos = reinterpret_cast<uint16_t*>(p);    p += align16((size_t)H * 2);
     int32_t* kcol = reinterpret_cast<int32_t*>(p);      p += align16((size_t)KM * 4);
     int32_t* kps = reinterpret_cast<int32_t*>(p);       p += align16((size_t)KM * 4);
@@ -607,7 +614,7 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
     T* kval_u = q_s;
 
     for (int i = tid; i < kHistWin; i += nth) win[i] = 0u;
-    for (int i = tid; i < H; i += nth) { hkey[i] = -1; hcnt[i] = 0; wmask[i] = 0ull; }
+    for (int i = tid; i < H; i += nth) { hkey[i] = -1; hcnt[i] = 0; wmask[i] = (WMask)0; }
     if (tid == 0) { s_wn = 0u; s_slot_left = 0ull; s_pool_left = 0ull; s_slot_base = 0ull; s_pool_base = 0ull; }
     pdl_wait();
     WalkState* st = a.st;
@@ -902,15 +909,15 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
         const int dpos = hpos[find(dcol)];
         __syncthreads();
         // ---- P4: the products into the staging lists, in stream order, one window of 32 operands at a time
-        for (int w0 = 0; w0 < nk; w0 += 64) {
-            const int i_lo = kpre[w0], i_hi = kpre[min(w0 + 64, nk)];
-            for (int i = i_lo + tid; i < i_hi; i += nth) atomicOr(&wmask[pslot[i]], 1ull << ((int)pk[i] - w0));
+        for (int w0 = 0; w0 < nk; w0 += kWinOps) {
+            const int i_lo = kpre[w0], i_hi = kpre[min(w0 + kWinOps, nk)];
+            for (int i = i_lo + tid; i < i_hi; i += nth) atomicOr(&wmask[pslot[i]], (WMask)1 << ((int)pk[i] - w0));
             __syncthreads();
             for (int i = i_lo + tid; i < i_hi; i += nth) {
                 const int sl = pslot[i], k = pk[i];
-                const unsigned long long bit = 1ull << (k - w0);
+                const WMask bit = (WMask)1 << (k - w0);
                 const int pos = hpos[sl];
-                const int at = bptr_s[pos >> 5] + cptr[pos] + hcnt[sl] + __popcll(wmask[sl] & (bit - 1ull));
+                const int at = bptr_s[pos >> 5] + cptr[pos] + hcnt[sl] + wmask_popc(wmask[sl] & (WMask)(bit - 1));
                 CRWR_CHECK(st, at >= 0 && at < nprod, 9);
                 tck[at] = kpos[k];
                 tcw[at] = __ldg(pvals + kps[k] + (i - kpre[k]));
@@ -918,10 +925,10 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
             __syncthreads();
             for (int i = i_lo + tid; i < i_hi; i += nth) {
                 const int sl = pslot[i];
-                const unsigned long long m = wmask[sl];
-                const unsigned long long bit = 1ull << ((int)pk[i] - w0);
+                const WMask m = wmask[sl];
+                const WMask bit = (WMask)1 << ((int)pk[i] - w0);
                 // the output's first product of the window updates its fill level (a later one may already see the mask cleared)
-                if (m != 0ull && (m & (bit - 1ull)) == 0ull) { hcnt[sl] += __popcll(m); wmask[sl] = 0ull; }
+                if (m != 0 && (m & (WMask)(bit - 1)) == 0) { hcnt[sl] += wmask_popc(m); wmask[sl] = (WMask)0; }
             }
             __syncthreads();
         }

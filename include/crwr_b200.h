@@ -87,7 +87,7 @@ typedef struct crwr_status {
     int32_t capacity_overflow;  /* bit 0: an iterate buffer overflowed, bit 1: candidate buffer overflowed (results invalid);
                                  * bit 2: sharded walk only - the select window missed, call crwr_walk_redo */
     int32_t fallback_rows;      /* rows that took the large-row path in the last step */
-    int64_t nnz_iterate;        /* entries currently stored (before the last cut) */
+    int64_t nnz_iterate;        /* entries stored by the last step's product (before its cut) */
     int64_t max_row_len;        /* longest stored row */
     int64_t max_kept;           /* longest kept (post-cut) operand row read by the last step */
     double last_cut;
@@ -128,6 +128,12 @@ int32_t crwr_walk_init(crwr_handle h, double rp, double perc, double tol, int32_
  * large-row path, so hints affect speed only, never results.  Host policy derives them from
  * crwr_status.max_row_len / max_kept. */
 int32_t crwr_set_row_hints(crwr_handle h, int64_t max_row_len, int64_t max_kept);
+/* Host policy for the settled-walk form of the select (one single-CTA kernel per step working on a window around the
+ * previous cut): no such step before walk step `until_step` (0: the library's default, from step 6 on).  While the cut
+ * still moves by a large factor per step no window can be set and that kernel would have to select over the whole value
+ * array by itself; the multi-CTA histogram select of the first steps is kept instead.  Speed only, never results;
+ * cleared by crwr_walk_init. */
+int32_t crwr_hold_window_select(crwr_handle h, int32_t until_step);
 int64_t crwr_transition_nnz(crwr_handle h);
 /* Current kernel sizing (diagnostics): {H, limit, kmax, scap, warps/CTA, smem bytes/warp, grid, SMs}. */
 int32_t crwr_get_shape(crwr_handle h, int64_t* h_out8);

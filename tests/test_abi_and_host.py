@@ -122,6 +122,14 @@ def test_shard_rows_partitions():
         crwr.shard_rows(3, 4)
 
 
+def test_expanding_walk_policy():
+    """(steps issued, entries of the last product, cut) at the polls after walk steps 1 and 3, as recorded on the B200."""
+    assert not crwr.expanding_walk((2, 533006, 8.104e-3), (4, 720825, 3.536e-3))          # c3_sparse, rwr-thres 80
+    assert not crwr.expanding_walk((2, 10177701, 1.307e-3), (4, 19874412, 3.899e-4))      # c4_dense, rwr-thres 80
+    assert crwr.expanding_walk((2, 533006, 1.509e-3), (4, 1626742, 1.405e-4))             # c3_sparse, rwr-thres 50
+    assert not crwr.expanding_walk((2, 0, 0.0), (4, 10, 1e-3))                            # nothing to compare yet
+
+
 def test_next_row_hints_policy():
     assert crwr.next_row_hints(0, 0, 80, 0) == (192, 32)
     out, kept = crwr.next_row_hints(30, 1, 80, 1)            # un-cut step-0 rows feed step 1
