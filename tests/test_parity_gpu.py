@@ -506,6 +506,37 @@ def test_densities_between_the_bench_workloads_change_no_bit(cuda_device, genome
     assert _bit_equal(it, it0)
 
 
+def test_expanding_walk_keeps_the_histogram_select_and_changes_no_bit(cuda_device, monkeypatch):
+    """rwr-thres 50: rows double per step and the cut falls several-fold - the host holds the window select for such a
+    walk (crwr.expanding_walk -> crwr_hold_window_select).  Same bits as with the policy switched off."""
+    from imputecc_b200 import crwr as crwr_mod
+    M, idx = synth.make_workload(synth.Workload("exp", 6000, 960, 100, 16))
+    seen = []
+    real = crwr_mod.expanding_walk
+
+    def spy(prev, now):
+        seen.append(real(prev, now))
+        return seen[-1]
+
+    def walk50():
+        n, m = M.shape[0], idx.size
+        w = pkg.Walker(n, m, dtype=np.float32, device=cuda_device, transition_nnz_cap=M.nnz + n)
+        try:
+            w.build_transition(M.indptr, M.indices, M.data, pkg.markers_first_order(n, idx))
+            st = w.walk(0.5, 50)
+            return int(st.steps_done), w.iterate(), w.trace()
+        finally:
+            w.close()
+
+    monkeypatch.setattr(crwr_mod, "expanding_walk", spy)
+    steps, it, tr = walk50()
+    assert seen and seen[-1] is True
+    monkeypatch.setattr(crwr_mod, "expanding_walk", lambda prev, now: False)
+    steps0, it0, tr0 = walk50()
+    assert steps == steps0 and _trace_key(tr) == _trace_key(tr0)
+    assert _bit_equal(it, it0)
+
+
 def test_deferred_rows_behind_a_window_step_are_retried(cuda_device):
     """Tiny accumulator hints from walk step 4 on: rows are deferred in a window-select step that queued no large-row
     kernel; the finish step flags it, the host walks again with the kernel queued, and the result is unchanged."""
