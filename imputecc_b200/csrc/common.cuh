@@ -213,6 +213,8 @@ struct RowStruct {
     int32_t step;           // last walk step that wrote the row in structure order into its slot
     int32_t hot_bytes;      // bytes of the block's hot part (what the fast kernel stages in shared memory)
     int32_t groups;         // groups the outputs are dealt to (1, or kBigGroups for a long row)
+    int32_t blk_cap;        // bytes the row's pool block can hold (a rebuilt structure that fits stays in place)
+    int32_t slot_cap;       // entries the row's fixed slot can hold
 };
 
 template <typename T>

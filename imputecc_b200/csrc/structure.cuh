@@ -858,31 +858,42 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
         if (no > a.small_no || struct_layout<T>(no, nprod, 1).hot_bytes > (uint32_t)a.small_hot) G = kBigGroups;
         const StructLayout L = struct_layout<T>(no, nprod, G);
         const unsigned long long no4 = (unsigned long long)((no + 3) & ~3);     // slots start on 16-byte boundaries (bulk copies)
-        if (!defer) {
+        // A rebuilt structure that fits the row's old block and slot stays in place (blocks and slots are never handed
+        // back during a walk, and a slowly settling walk rebuilds thousands of rows in its first steps); new ones are
+        // reserved with a quarter to spare for that.
+        const bool reuse = !defer && had_slot && (unsigned long long)L.bytes <= (unsigned long long)old.blk_cap &&
+                           no4 <= (unsigned long long)old.slot_cap;
+        const unsigned long long want_slot = reuse ? (unsigned long long)old.slot_cap : ((no4 + no4 / 4 + 3ull) & ~3ull);
+        const unsigned long long want_blk = reuse ? (unsigned long long)old.blk_cap
+                                                  : (((unsigned long long)L.bytes + (unsigned long long)L.bytes / 4 + 15ull) & ~15ull);
+        if (reuse) {
+            slot_rel = (unsigned long long)(old.slot - a.fixed_base);
+            poff = (unsigned long long)old.off;
+        } else if (!defer) {
             // ---- reservations: fixed slot in both iterate buffers, pool block (thread 0; chunked while many rows are built)
-            if (no4 > s_slot_left) zero_slots(s_slot_base, s_slot_left);
+            if (want_slot > s_slot_left) zero_slots(s_slot_base, s_slot_left);
             __syncthreads();
             if (tid == 0) {
-                if (no4 > s_slot_left) {
-                    const unsigned long long sz = (chunked && (unsigned long long)a.slot_chunk > no4) ? (unsigned long long)a.slot_chunk : no4;
+                if (want_slot > s_slot_left) {
+                    const unsigned long long sz = (chunked && (unsigned long long)a.slot_chunk > want_slot) ? (unsigned long long)a.slot_chunk : want_slot;
                     s_slot_base = atomicAdd(&st->slot_cursor, sz);
                     s_slot_left = sz;
                 }
-                s_slot_rel = s_slot_base; s_slot_base += no4; s_slot_left -= no4;
-                if ((unsigned long long)L.bytes > s_pool_left) {
-                    const unsigned long long sz = (chunked && (unsigned long long)a.pool_chunk > (unsigned long long)L.bytes) ? (unsigned long long)a.pool_chunk : (unsigned long long)L.bytes;
+                s_slot_rel = s_slot_base; s_slot_base += want_slot; s_slot_left -= want_slot;
+                if (want_blk > s_pool_left) {
+                    const unsigned long long sz = (chunked && (unsigned long long)a.pool_chunk > want_blk) ? (unsigned long long)a.pool_chunk : want_blk;
                     s_pool_base = atomicAdd(&st->pool_cursor, sz);
                     s_pool_left = sz;
                 }
-                s_poff = s_pool_base; s_pool_base += (unsigned long long)L.bytes; s_pool_left -= (unsigned long long)L.bytes;
+                s_poff = s_pool_base; s_pool_base += want_blk; s_pool_left -= want_blk;
             }
             __syncthreads();
             slot_rel = s_slot_rel; poff = s_poff;
-            if (slot_rel + no4 > (unsigned long long)a.slot_cap || poff + L.bytes > a.pool_cap) {
+            if (slot_rel + want_slot > (unsigned long long)a.slot_cap || poff + want_blk > a.pool_cap) {
                 // slot region or pool exhausted: the row goes without a structure (large-row kernel), this step and - as
                 // the cursors only grow - every later one; struct_full tells the host a larger workspace would be faster
                 if (tid == 0) st->struct_full = 1;
-                zero_slots(slot_rel, no4);          // the slot entries it did get stay empty
+                zero_slots(slot_rel, want_slot);    // the slot entries it did get stay empty
                 defer = true;
             }
         }
@@ -897,7 +908,9 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
         const long long slot = a.fixed_base + (long long)slot_rel;
         unsigned char* blk = a.pool + poff;
         const int nb = (no + 31) >> 5;
-        if (tid < (int)no4 - no) { a.in.vals[slot + no + tid] = (T)0; a.out.vals[slot + no + tid] = (T)0; }
+        // (everything of the slot beyond the row's entries is zero in both buffers: a new slot's spare part here; a reused
+        // slot's was cleared when it was reserved, and its old entries above and below)
+        if (!reuse) for (int i = no + tid; i < (int)want_slot; i += nth) { a.in.vals[slot + i] = (T)0; a.out.vals[slot + i] = (T)0; }
         if (had_slot) for (int i = tid; i < old.no; i += nth) a.in.vals[old.slot + i] = (T)0;
         // positions of the operands, K+ membership bits, previous values in structure order
         for (int i = tid; i < nk; i += nth) {
@@ -1026,6 +1039,7 @@ __global__ void __launch_bounds__(512) symbolic_kernel(PropArgs<T> a, SymShape s
             RowStruct hd;
             hd.off = (long long)poff; hd.slot = slot; hd.no = no; hd.nprod = nprod; hd.nk = nk; hd.dpos = dpos;
             hd.gen = gen; hd.step = step; hd.hot_bytes = (int32_t)L.hot_bytes; hd.groups = G;
+            hd.blk_cap = (int32_t)want_blk; hd.slot_cap = (int32_t)want_slot;
             a.rs[row] = hd;
             a.out.row_ptr[row] = slot;
             a.out.row_len[row] = no;

@@ -439,6 +439,7 @@ __global__ void __launch_bounds__(kWarpSymMaxWarps * 32) symbolic_warp_kernel(Pr
             RowStruct hd;
             hd.off = (long long)poff; hd.slot = slot; hd.no = no; hd.nprod = nprod; hd.nk = nk; hd.dpos = dpos;
             hd.gen = gen; hd.step = step; hd.hot_bytes = (int32_t)L.hot_bytes; hd.groups = 1;
+            hd.blk_cap = (int32_t)L.bytes; hd.slot_cap = (int32_t)no4;
             a.rs[row] = hd;
             a.out.row_ptr[row] = slot;
             a.out.row_len[row] = no;
