@@ -523,7 +523,7 @@ int configure_group_shape(crwr_handle_s* h, long long max_row_len, long long max
     // often and spill several products per overflowing column: a quarter instead of an eighth removes the large-row
     // fallbacks of c4_dense (24 -> 1 rows per walk, -10 % per step) and of 220-contig genomes (10 rows in every step,
     // +35 % per walk); short rows keep the smaller list (it would cost them a CTA per SM).
-    long long ov_div = want > 384 ? 4 : 8;
+    long long ov_div = want > 320 ? 4 : 8;
     if (const char* e = getenv("CRWR_GROUP_OV_DIV")) { const int v = atoi(e); if (v >= 1 && v <= 64) ov_div = v; }
     // table, kept list and CTA size for one table load
     auto make = [&](int load_pct, long long* in_flight) -> GroupShape {
