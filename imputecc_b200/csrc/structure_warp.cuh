@@ -1,18 +1,21 @@
-// K2, symbolic part for SHORT rows: the structure of structure.cuh built by ONE WARP per row.
+// K2, symbolic part for SHORT rows: the structure of structure.cuh built by ONE WARP per row - used for the FIRST
+// build of a walk (every row at once), when the rows average at most ~110 stored entries.
 //
 // symbolic_kernel gives a row a whole CTA; a short row (a few dozen operands, a few hundred products) leaves most of
-// its threads idle behind block-wide barriers, and the ~18 us a CTA needs per row land on the critical path of every
-// walk step in which a few rows leave their structure.  Here a warp keeps everything of its row in a private region
-// of shared memory, synchronises with __syncwarp only, and - because the warp walks the row's products in stream
-// order (operand column ascending) - the products of an output fall into their summation order by themselves: the
-// place of a product is its output's fill level plus its rank among the products of the same output in the same
-// batch of 32 (match_any).  The products go straight to their final position of the group stream (round tables: how
-// many lanes are still active in round j, how many products the rounds before j hold), the hot part of the pool
-// block is assembled in shared memory in its pool layout, copied out in 16-byte pieces, and replayed on the spot by
-// the same numeric_stream the fast kernel uses.
+// its threads idle behind block-wide barriers: 425 us for the first build of 8,000 such rows.  Here a warp keeps
+// everything of its row in a private region of shared memory (~17 KB, sized from the MEAN row: 12-14 rows in flight per
+// SM), synchronises with __syncwarp only, and - because the warp walks the row's products in stream order (operand
+// column ascending) - the products of an output fall into their summation order by themselves: the place of a product
+// is its output's fill level plus its rank among the products of the same output in the same batch of 32 (match_any).
+// The products go straight to their final position of the group stream (round tables: how many lanes are still
+// active in round j, how many products the rounds before j hold), the hot part of the pool block is assembled in
+// shared memory in its pool layout, copied out in 16-byte pieces, and replayed on the spot by the same numeric_stream
+// the fast kernel uses.  120 us for the same 8,000 rows.
 //
 // Rows that exceed the warp's tables (operands, products, outputs, rounds) or would need several groups are handed to
-// symbolic_kernel through a second list, untouched.
+// symbolic_kernel through a second list, untouched.  A SINGLE row is built sooner by a CTA (~15 us against ~35 us for
+// one warp: the chain of dependent shared-memory steps is the same, the CTA has more lanes per step), so the short
+// lists of later walk steps - the rows whose kept set left their structure - go to symbolic_kernel directly.
 #pragma once
 #include "structure.cuh"
 
